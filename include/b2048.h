@@ -1,0 +1,194 @@
+/*
+ * b2048.h — C-ABI of the B200-native 2048 / Double-DQN hot path.
+ *
+ * This is the drop-in boundary for the reference's `board.Board2048` environment step and the
+ * `dqn_lib` experience/update loop (ribal-aladeeb/reinforcement-learning-2048).  The reference has
+ * no FFI of its own (it is pure Python), so every entry point below cites the
+ * reference Python it replaces (paths relative to the reference root).  The Python shims
+ * `board.py` / `dqn_lib.py` in this repo bind these symbols with ctypes.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / C++ types;
+ *   - pointers are DEVICE pointers owned by the caller unless the name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - return value is an `int`: 0 = ok, >0 = a `cudaError_t`, <0 = a B2048_E* code below;
+ *   - device-pointer calls never allocate, never synchronise and never throw after
+ *     `b2048_init(device)`; they are safe to capture in a CUDA graph;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Packed board format ("u64 board"): 16 tile exponents of 4 bits each; cell (row r, column c)
+ * lives in nibble 4*r + c, nibble 0 = least-significant.  Exponent 0 = empty, e>0 = tile 2^e
+ * (this is exactly the reference's `log_scale()` value, src/board.py:224-231).  Row-major nibble
+ * order makes "k-th empty cell" agree with the reference's `np.where(state == 0)` order
+ * (src/board.py:46-48).
+ *
+ * Action encoding everywhere: 0 = up, 1 = down, 2 = left, 3 = right (src/board.py:129,191).
+ */
+#ifndef B2048_H_
+#define B2048_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2048_ABI_VERSION 1
+
+/* ---- error codes (negative; positive values are cudaError_t) ------------------------------ */
+#define B2048_OK 0
+#define B2048_ENOTINIT (-1)  /* b2048_init(device) has not been called for the current device */
+#define B2048_EINVAL   (-2)  /* bad argument (NULL pointer, negative size, bad device, ...)    */
+#define B2048_ENODEV   (-3)  /* no usable CUDA device                                         */
+
+/* ---- flags byte written by the step / legal-mask kernels ---------------------------------- */
+#define B2048_FLAG_UP       0x01u /* bits 0-3: legal-move mask of the INPUT board,            */
+#define B2048_FLAG_DOWN     0x02u /*   order [up, down, left, right]                          */
+#define B2048_FLAG_LEFT     0x04u /*   (src/board.py:128-135)                                 */
+#define B2048_FLAG_RIGHT    0x08u
+#define B2048_FLAG_DONE     0x10u /* INPUT board has no legal move (src/dqn_lib.py:17-18)     */
+#define B2048_FLAG_CHANGED  0x20u /* the move changed the board => a tile was spawned         */
+#define B2048_FLAG_OVERFLOW 0x40u /* a 32768+32768 merge happened: 2^16 does not fit 4 bits;  */
+                                  /*   next/reward for that board are unspecified             */
+#define B2048_FLAG_BADSPAWN 0x80u /* spawn_override named a non-empty cell (nothing spawned)  */
+
+/* spawn_override byte: low nibble = cell index 4*r+c, high nibble = exponent (1 => "2",
+ * 2 => "4"); 0xFF = no override for this board (use the Philox stream). */
+#define B2048_SPAWN_NONE 0xFFu
+
+/* p4_threshold: a spawned tile is a "4" iff a fresh 32-bit Philox word is < p4_threshold.
+ * 0x1999999A = 10 % (north_star), 0x80000000 = 50 % (the reference, src/board.py:12,49). */
+#define B2048_P4_TEN_PERCENT   0x1999999Au
+#define B2048_P4_FIFTY_PERCENT 0x80000000u
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Build the 65536-entry row table (canonical left slide+merge, = src/board.py:92-126 for every
+ * row of 4-bit exponents) and upload it to `device`; allocate the small reduction scratch used
+ * by ddqn_target_loss.  Idempotent, thread-safe.  Must precede every other call on `device`. */
+int b2048_init(int device);
+int b2048_shutdown(int device);
+int b2048_abi_version(void);
+const char* b2048_error_string(int code);
+
+/* Copy the 65536 x u32 row table to host memory (tests compare it with the oracle).
+ * entry = result_row16 | (merge_reward/4) << 16 | overflow << 31. */
+int b2048_copy_row_lut_host(uint32_t* out65536);
+
+/* ---- K1: environment step ------------------------------------------------------------------ */
+
+/* One action per board.  Replaces Board2048.peek_action (src/board.py:185-202) -> up/down/left/
+ * right (:147-183) -> _apply_action_to_vector (:92-126) -> _populate_empty_cell (:41-51),
+ * dqn_lib.reward_func_merge_score (src/dqn_lib.py:87-88) and the legal-mask / done test of
+ * epsilon_greedy_policy (src/dqn_lib.py:17-18) for n boards at once.
+ *   next[i]   = slide/merge of boards[i] by actions[i], plus one spawned tile iff changed
+ *   reward[i] = sum of merged tile values of this move
+ *   flags[i]  = B2048_FLAG_* (legal mask and done are properties of the INPUT board)
+ * Spawn: cell = k-th empty cell (row-major) with k uniform from Philox4x32-10 keyed by `seed`,
+ * counter (global board index = index_base + i, `step`); value "4" iff word < p4_threshold.
+ * spawn_override (nullable, n bytes) replays a given (cell, value) instead — the parity hook.
+ * actions[i] > 3 is treated as actions[i] & 3. */
+int b2048_step(const uint64_t* boards, const uint8_t* actions, uint64_t* next, int32_t* reward,
+               uint8_t* flags, int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
+               uint32_t p4_threshold, const uint8_t* spawn_override, void* stream);
+
+/* All four actions per board (BASELINE.json config 2; = Board2048.available_moves,
+ * src/board.py:138-145).  next4[i*4+a], reward4[i*4+a]; flags[i] bits 0-3 = legal mask, bit 4 =
+ * done, bit 6 = overflow in any direction.  Successor a equals b2048_step's output for action a
+ * (same Philox words).  spawn_override4 (nullable) is n*4 bytes. */
+int b2048_step_all4(const uint64_t* boards, uint64_t* next4, int32_t* reward4, uint8_t* flags,
+                    int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
+                    uint32_t p4_threshold, const uint8_t* spawn_override4, void* stream);
+
+/* Legal mask + done only (= available_moves_as_torch_unit_vector, src/board.py:128-135). */
+int b2048_legal_mask(const uint64_t* boards, uint8_t* flags, int64_t n, void* stream);
+
+/* Fresh boards: zeros + two spawns (= Board2048.__init__, src/board.py:10-20).  If `where_flags`
+ * is non-NULL only boards with (where_flags[i] & B2048_FLAG_DONE) are reset (episode auto-reset,
+ * src/dqn_lib.py:176). */
+int b2048_reset(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
+                uint32_t p4_threshold, const uint8_t* where_flags, void* stream);
+
+/* int64 tiles [n,16] (reference `state`, row-major) <-> packed boards.  bad[i] (nullable) is set
+ * to 1 if a tile is not 0 or a power of two in 2..32768. */
+int b2048_pack(const int64_t* tiles, uint64_t* boards, uint8_t* bad, int64_t n, void* stream);
+int b2048_unpack_tiles(const uint64_t* boards, int64_t* tiles, int64_t n, void* stream);
+/* Network input layout: exponents as float64, [n,16] == [n,1,4,4] contiguous
+ * (= log_scale().state_as_4d_tensor() / flattened_state_as_tensor(), src/board.py:224-237). */
+int b2048_unpack_f64(const uint64_t* boards, double* out, int64_t n, void* stream);
+
+/* Synthetic inputs of SURVEY.md §8(d): each cell empty with probability p_empty_threshold/2^32,
+ * else exponent uniform in 1..max_exp; actions uniform in 0..3. */
+int b2048_random_boards(uint64_t* boards, int64_t n, uint64_t seed, uint64_t index_base,
+                        uint32_t p_empty_threshold, uint32_t max_exp, void* stream);
+int b2048_random_actions(uint8_t* actions, int64_t n, uint64_t seed, uint64_t step,
+                         uint64_t index_base, void* stream);
+
+/* Same as b2048_step but with HOST buffers: chunks the batch and overlaps H2D copy, kernel and
+ * D2H copy on internal streams; returns after everything has landed in the host buffers.
+ * Allocates its device workspace lazily on first use (per device). */
+int b2048_step_host(const uint64_t* h_boards, const uint8_t* h_actions, uint64_t* h_next,
+                    int32_t* h_reward, uint8_t* h_flags, int64_t n, uint64_t seed, uint64_t step,
+                    uint64_t index_base, uint32_t p4_threshold, const uint8_t* h_spawn_override,
+                    int device);
+
+/* ---- K2: GPU-resident replay ring ------------------------------------------------------------ */
+
+/* Struct-of-arrays ring of `capacity` transitions (= the deque(maxlen) of 5-tuples,
+ * src/dqn_lib.py:106,172).  All arrays are caller-allocated device memory; `head_size` is a
+ * device int64[2] {head, size} that must be zero-initialised by the caller. */
+typedef struct b2048_ring {
+  uint64_t* s;        /* [capacity] packed state                 */
+  uint64_t* s2;       /* [capacity] packed next state            */
+  int32_t*  r;        /* [capacity] reward                       */
+  uint8_t*  a;        /* [capacity] action                       */
+  uint8_t*  d;        /* [capacity] done (0/1)                   */
+  int64_t*  head_size;/* device int64[2]: next write slot, number of valid entries */
+  int64_t   capacity;
+} b2048_ring;
+
+/* Append n transitions in order (oldest first); if n > capacity only the last `capacity` survive,
+ * like deque(maxlen).  `done_flags` holds step flags bytes or 0/1 values: done = (byte & 0x10) or
+ * (byte == 1). */
+int replay_append(const b2048_ring* ring, const uint64_t* s, const uint8_t* a, const int32_t* r,
+                  const uint64_t* s2, const uint8_t* done_flags, int64_t n, void* stream);
+
+/* Fused uniform sampling (with replacement) + gather + unpack into the network layout
+ * (= sample_experiences + extract_samples_conv/dense, src/dqn_lib.py:33-84).
+ * Logical index 0 = oldest entry, like deque indexing.  idx_override (nullable, int64[B]) replays
+ * the reference's np.random.randint draw; idx_out (nullable) receives the indices used.
+ * states/next_states: f64 [B,16]; actions/rewards/dones: int64 [B]. */
+int replay_sample(const b2048_ring* ring, int64_t B, uint64_t seed, uint64_t ctr,
+                  const int64_t* idx_override, double* states, double* next_states,
+                  int64_t* actions, int64_t* rewards, int64_t* dones, int64_t* idx_out,
+                  void* stream);
+
+/* ---- K3: fused Double-DQN target + summed-MSE ------------------------------------------------ */
+
+/* = src/dqn_lib.py:125-158.  a* = argmax_j q_next_online[i,j] (first index on ties);
+ * target[i] = rewards[i] + (double)((float)(1-dones[i]) * gamma_f32) * q_next_target[i,a*]
+ * (use_double != 0) or ... * max_j q_next_target[i,j] (use_double == 0; q_next_online may be NULL);
+ * q_sa[i] = q_cur[i, actions[i]]; loss[0] = sum_i (q_sa[i]-target[i])^2 (deterministic order);
+ * grad_q_cur (nullable) [B,4] = d loss / d q_cur = 2 (q_sa - target) at column actions[i], else 0.
+ * gamma is deliberately a float: the reference rounds it to float32. */
+int ddqn_target_loss(const double* q_next_online, const double* q_next_target, const double* q_cur,
+                     const int64_t* actions, const int64_t* rewards, const int64_t* dones,
+                     float gamma_f32, int use_double, double* target, double* q_sa, double* loss,
+                     double* grad_q_cur, int64_t B, void* stream);
+
+/* ---- K0: batched epsilon-greedy ---------------------------------------------------------------- */
+
+/* = epsilon_greedy_policy, src/dqn_lib.py:16-30, for n boards.  With probability eps the action is
+ * uniform in 0..3 ignoring legality and max_q = 0; otherwise
+ * action = argmax_j (legal_j ? (q_j - min(q)*max(q) - min(q)) : 0*(...)) with first-index ties and
+ * max_q = max_j q_j.  flags = step/legal-mask flags bytes (bits 0-3 legal).
+ * override (nullable, n bytes): 0xFF = draw from Philox, 0x80 = force greedy, 0..3 = force that
+ * random action — the parity hook for np.random.rand()/randint (src/dqn_lib.py:20-21). */
+int egreedy_select(const double* q, const uint8_t* flags, double eps, uint64_t seed, uint64_t ctr,
+                   uint64_t index_base, const uint8_t* override_bytes, uint8_t* actions,
+                   double* max_q, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2048_H_ */

@@ -1,0 +1,219 @@
+"""Batched Board2048 operations on CUDA tensors (thin wrappers over include/b2048.h).
+
+Boards are ``torch.int64`` CUDA tensors holding the packed-u64 bit pattern (nibble 4r+c = tile
+exponent).  All functions launch on torch's current stream of the tensors' device and never
+synchronise; outputs can be preallocated (``out=`` arguments) for CUDA-graph capture.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+P4_TEN_PERCENT = 0x1999999A      # north_star: 2 at 90 %, 4 at 10 %
+P4_FIFTY_PERCENT = 0x80000000    # the reference: np.random.choice([2, 4]) (src/board.py:12,49)
+
+FLAG_LEGAL = 0x0F
+FLAG_DONE, FLAG_CHANGED, FLAG_OVERFLOW, FLAG_BADSPAWN = 0x10, 0x20, 0x40, 0x80
+SPAWN_NONE = 0xFF
+
+_U64 = (1 << 64) - 1
+
+
+def p4_threshold(p: float) -> int:
+    """Probability that a spawned tile is a 4 -> 32-bit threshold."""
+    return max(0, min(0xFFFFFFFF, int(round(p * 4294967296.0))))
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise _lib.B2048Error("b2048 needs CUDA tensors: there is no CPU fallback")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(t: torch.Tensor):
+    return _lib.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else _lib.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, dtype, n=None, name="tensor"):
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    if n is not None and t.numel() != n:
+        raise ValueError(f"{name}: expected {n} elements, got {t.numel()}")
+    return t
+
+
+def step(boards, actions, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT, spawn_override=None,
+         out=None):
+    """One action per board -> (next int64[n], reward int32[n], flags uint8[n]).
+
+    = Board2048.peek_action + merge-score reward + legal mask/done of the input board
+    (src/board.py:185-202, src/dqn_lib.py:17-18, 87-88)."""
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    _chk(actions, torch.uint8, n, "actions")
+    if out is None:
+        out = (torch.empty_like(boards), torch.empty(n, dtype=torch.int32, device=boards.device),
+               torch.empty(n, dtype=torch.uint8, device=boards.device))
+    nxt, reward, flags = out
+    _chk(nxt, torch.int64, n, "next"); _chk(reward, torch.int32, n, "reward"); _chk(flags, torch.uint8, n, "flags")
+    if spawn_override is not None:
+        _chk(spawn_override, torch.uint8, n, "spawn_override")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_step(_ptr(boards), _ptr(actions), _ptr(nxt), _ptr(reward), _ptr(flags), n,
+                                         seed & _U64, step_index & _U64, index_base & _U64, p4,
+                                         _ptr(spawn_override), _stream(boards)), "b2048_step")
+    return nxt, reward, flags
+
+
+def step_all4(boards, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT, spawn_override4=None, out=None):
+    """All four successors -> (next4 int64[n,4], reward4 int32[n,4], flags uint8[n]).
+    = Board2048.available_moves (src/board.py:138-145)."""
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    if out is None:
+        out = (torch.empty((n, 4), dtype=torch.int64, device=boards.device),
+               torch.empty((n, 4), dtype=torch.int32, device=boards.device),
+               torch.empty(n, dtype=torch.uint8, device=boards.device))
+    nxt, reward, flags = out
+    _chk(nxt, torch.int64, 4 * n, "next4"); _chk(reward, torch.int32, 4 * n, "reward4"); _chk(flags, torch.uint8, n, "flags")
+    if spawn_override4 is not None:
+        _chk(spawn_override4, torch.uint8, 4 * n, "spawn_override4")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_step_all4(_ptr(boards), _ptr(nxt), _ptr(reward), _ptr(flags), n,
+                                              seed & _U64, step_index & _U64, index_base & _U64, p4,
+                                              _ptr(spawn_override4), _stream(boards)), "b2048_step_all4")
+    return nxt, reward, flags
+
+
+def legal_mask(boards, out=None):
+    """flags uint8[n]: bits 0-3 legal [up,down,left,right], bit 4 done (src/board.py:128-135)."""
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    flags = out if out is not None else torch.empty(n, dtype=torch.uint8, device=boards.device)
+    _chk(flags, torch.uint8, n, "flags")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_legal_mask(_ptr(boards), _ptr(flags), n, _stream(boards)), "b2048_legal_mask")
+    return flags
+
+
+def reset(boards, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT, where_flags=None):
+    """In place: fresh boards (zeros + two spawns, src/board.py:10-20); with `where_flags` only
+    the boards whose DONE bit is set."""
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    if where_flags is not None:
+        _chk(where_flags, torch.uint8, n, "where_flags")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_reset(_ptr(boards), n, seed & _U64, step_index & _U64, index_base & _U64, p4,
+                                          _ptr(where_flags), _stream(boards)), "b2048_reset")
+    return boards
+
+
+def new_boards(n, device="cuda", **kw):
+    return reset(torch.empty(n, dtype=torch.int64, device=device), **kw)
+
+
+def pack(tiles, check=True):
+    """int64 tile values [n,16] / [n,4,4] (reference `state`) -> packed boards int64[n]."""
+    tiles = tiles.contiguous()
+    n = tiles.numel() // 16
+    dev = _dev(tiles)
+    _lib.init(dev)
+    _chk(tiles, torch.int64, 16 * n, "tiles")
+    boards = torch.empty(n, dtype=torch.int64, device=tiles.device)
+    bad = torch.empty(n, dtype=torch.uint8, device=tiles.device) if check else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_pack(_ptr(tiles), _ptr(boards), _ptr(bad), n, _stream(tiles)), "b2048_pack")
+    if check and bool(bad.any()):
+        raise ValueError("pack: tiles must be 0 or powers of two in 2..32768 (4-bit exponents)")
+    return boards
+
+
+def unpack_tiles(boards):
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    out = torch.empty((n, 16), dtype=torch.int64, device=boards.device)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_unpack_tiles(_ptr(boards), _ptr(out), n, _stream(boards)), "b2048_unpack_tiles")
+    return out
+
+
+def unpack_f64(boards, out=None, conv=False):
+    """Network input: exponents as float64 [n,16] (dense) or [n,1,4,4] (conv) — the same bytes
+    (src/board.py:224-237, src/dqn_lib.py:8-13)."""
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    if out is None:
+        out = torch.empty((n, 16), dtype=torch.float64, device=boards.device)
+    _chk(out, torch.float64, 16 * n, "out")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_unpack_f64(_ptr(boards), _ptr(out), n, _stream(boards)), "b2048_unpack_f64")
+    return out.view(n, 1, 4, 4) if conv else out.view(n, 16)
+
+
+def random_boards(n, seed=2048, index_base=0, p_empty=0.3, max_exp=11, device="cuda", out=None):
+    """Synthetic boards of SURVEY.md §8(d): cell empty w.p. p_empty else exponent uniform 1..max_exp."""
+    boards = out if out is not None else torch.empty(n, dtype=torch.int64, device=device)
+    dev = _dev(boards)
+    _lib.init(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_random_boards(_ptr(boards), n, seed & _U64, index_base & _U64,
+                                                  p4_threshold(p_empty), max_exp, _stream(boards)),
+                   "b2048_random_boards")
+    return boards
+
+
+def random_actions(n, seed=2050, step_index=0, index_base=0, device="cuda", out=None):
+    actions = out if out is not None else torch.empty(n, dtype=torch.uint8, device=device)
+    dev = _dev(actions)
+    _lib.init(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_random_actions(_ptr(actions), n, seed & _U64, step_index & _U64,
+                                                   index_base & _U64, _stream(actions)), "b2048_random_actions")
+    return actions
+
+
+def step_host(boards, actions, nxt, reward, flags, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT,
+              spawn_override=None, device=0):
+    """b2048_step with HOST buffers (numpy arrays or CPU tensors, ideally pinned): the library
+    chunks the batch and overlaps H2D, kernel and D2H.  Blocks until the results are in `nxt`,
+    `reward`, `flags`."""
+    _lib.init(device)
+
+    def hp(a):
+        if a is None:
+            return None
+        if isinstance(a, np.ndarray):
+            return _lib.c_void_p(a.ctypes.data)
+        return _lib.c_void_p(a.data_ptr())
+
+    n = int(boards.shape[0])
+    _lib.check(_lib.lib().b2048_step_host(hp(boards), hp(actions), hp(nxt), hp(reward), hp(flags), n,
+                                          seed & _U64, step_index & _U64, index_base & _U64, p4,
+                                          hp(spawn_override), device), "b2048_step_host")
+    return nxt, reward, flags
+
+
+def row_lut_host() -> np.ndarray:
+    """The 65536-entry row table as built on the host (no GPU needed)."""
+    out = np.zeros(65536, dtype=np.uint32)
+    _lib.check(_lib.lib().b2048_copy_row_lut_host(_lib.c_void_p(out.ctypes.data)), "b2048_copy_row_lut_host")
+    return out

@@ -1,0 +1,72 @@
+"""GPU-resident ring replay buffer (K2) — the deque(maxlen) of src/dqn_lib.py:172 as packed
+struct-of-arrays tensors with device-side head/size counters (CUDA-graph friendly)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from .env import _chk, _dev, _ptr, _stream, _U64
+
+
+class ReplayRing:
+    """Ring of `capacity` transitions (state, action, reward, next_state, done) on one GPU.
+
+    Logical index 0 is the oldest entry, exactly like indexing the reference's deque, so the
+    reference's ``np.random.randint(len(buf), size=B)`` draw can be replayed via `idx_override`.
+    """
+
+    def __init__(self, capacity: int, device="cuda"):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.init(dev)
+        self._dev = dev
+        kw = dict(device=self.device)
+        self.s = torch.zeros(self.capacity, dtype=torch.int64, **kw)
+        self.s2 = torch.zeros(self.capacity, dtype=torch.int64, **kw)
+        self.r = torch.zeros(self.capacity, dtype=torch.int32, **kw)
+        self.a = torch.zeros(self.capacity, dtype=torch.uint8, **kw)
+        self.d = torch.zeros(self.capacity, dtype=torch.uint8, **kw)
+        self.head_size = torch.zeros(2, dtype=torch.int64, **kw)
+        self._ring = _lib.Ring(self.s.data_ptr(), self.s2.data_ptr(), self.r.data_ptr(), self.a.data_ptr(),
+                               self.d.data_ptr(), self.head_size.data_ptr(), self.capacity)
+
+    def __len__(self) -> int:          # synchronises (reads the device counter)
+        return int(self.head_size[1].item())
+
+    def append(self, s, a, r, s2, done_flags) -> None:
+        """Append n transitions (src/dqn_lib.py:106).  `done_flags`: step flags bytes or 0/1."""
+        n = s.numel()
+        _chk(s, torch.int64, name="s"); _chk(s2, torch.int64, n, "s2"); _chk(a, torch.uint8, n, "a")
+        _chk(r, torch.int32, n, "r"); _chk(done_flags, torch.uint8, n, "done")
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.lib().replay_append(ctypes.byref(self._ring), _ptr(s), _ptr(a), _ptr(r), _ptr(s2),
+                                                _ptr(done_flags), n, _stream(s)), "replay_append")
+
+    def sample(self, batch_size: int, seed=2051, ctr=0, idx_override=None, out=None, return_idx=False):
+        """Fused sample + gather + unpack (src/dqn_lib.py:33-84).
+        -> states f64[B,16], actions i64[B], rewards i64[B], next_states f64[B,16], dones i64[B]
+        (reference order: states, actions, rewards, next_states, dones)."""
+        B = int(batch_size)
+        kw = dict(device=self.device)
+        if out is None:
+            out = (torch.empty((B, 16), dtype=torch.float64, **kw), torch.empty(B, dtype=torch.int64, **kw),
+                   torch.empty(B, dtype=torch.int64, **kw), torch.empty((B, 16), dtype=torch.float64, **kw),
+                   torch.empty(B, dtype=torch.int64, **kw))
+        states, actions, rewards, next_states, dones = out
+        idx_out = torch.empty(B, dtype=torch.int64, **kw) if return_idx else None
+        if idx_override is not None:
+            _chk(idx_override, torch.int64, B, "idx_override")
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.lib().replay_sample(ctypes.byref(self._ring), B, seed & _U64, ctr & _U64,
+                                                _ptr(idx_override), _ptr(states), _ptr(next_states),
+                                                _ptr(actions), _ptr(rewards), _ptr(dones), _ptr(idx_out),
+                                                _stream(states)), "replay_sample")
+        if return_idx:
+            return states, actions, rewards, next_states, dones, idx_out
+        return states, actions, rewards, next_states, dones
+
+    def clear(self) -> None:
+        self.head_size.zero_()

@@ -1,0 +1,173 @@
+// ddqn_kernels.cu — K3: fused Double-DQN target + summed-MSE residual, K0: batched epsilon-greedy.
+//
+// K3 replaces src/dqn_lib.py:125-158 (argmax over online Q(s'), one-hot gather of target Q(s',a*),
+// r + gamma32*(1-done)*Q, one-hot gather of Q(s,a), MSELoss(reduction='sum')) with one kernel that
+// also emits d loss / d Q(s,.) for the autograd backward.  K0 replaces
+// epsilon_greedy_policy (src/dqn_lib.py:16-30) for n boards.  All arithmetic is float64 with the
+// reference's rounding points kept (explicit _rn intrinsics: no FMA contraction), and gamma is
+// applied as a float32 value exactly like the reference does.
+#include "b2048_common.cuh"
+
+namespace b2048 {
+namespace {
+
+constexpr int K3_THREADS = 256;
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+  // fixed-order tree: warp shuffle, then 8 warp partials added in order by thread 0
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < K3_THREADS / 32; ++w) s = __dadd_rn(s, sh[w]);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(K3_THREADS)
+    ddqn_target_loss_kernel(const double* __restrict__ qno, const double* __restrict__ qnt,
+                            const double* __restrict__ qc, const int64_t* __restrict__ actions,
+                            const int64_t* __restrict__ rewards, const int64_t* __restrict__ dones,
+                            float gamma, int use_double, double* __restrict__ target,
+                            double* __restrict__ q_sa, double* __restrict__ loss,
+                            double* __restrict__ grad, int64_t B, double* __restrict__ partials,
+                            unsigned int* __restrict__ ticket) {
+  __shared__ double sh[K3_THREADS / 32];
+  __shared__ bool is_last;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * K3_THREADS + threadIdx.x; i < B;
+       i += (int64_t)gridDim.x * K3_THREADS) {
+    const double2* t2 = reinterpret_cast<const double2*>(qnt + 4 * i);
+    const double2 ta = t2[0], tb = t2[1];
+    const double tq[4] = {ta.x, ta.y, tb.x, tb.y};
+    double nb;
+    if (use_double) {
+      const double2* o2 = reinterpret_cast<const double2*>(qno + 4 * i);
+      const double2 oa = o2[0], ob = o2[1];
+      const double oq[4] = {oa.x, oa.y, ob.x, ob.y};
+      int best = 0;
+      double bv = oq[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (oq[j] > bv) { bv = oq[j]; best = j; }  // strict '>' keeps the first maximum
+      nb = tq[best];
+    } else {
+      nb = fmax(fmax(tq[0], tq[1]), fmax(tq[2], tq[3]));
+    }
+    const float g32 = __fmul_rn((float)(1 - dones[i]), gamma);  // int64 * python float -> float32
+    const double tgt = __dadd_rn((double)rewards[i], __dmul_rn((double)g32, nb));
+    const int a = (int)(actions[i] & 3);
+    const double2* c2 = reinterpret_cast<const double2*>(qc + 4 * i);
+    const double2 ca = c2[0], cb = c2[1];
+    const double cq[4] = {ca.x, ca.y, cb.x, cb.y};
+    const double q = cq[a];
+    const double diff = __dsub_rn(q, tgt);
+    target[i] = tgt;
+    q_sa[i] = q;
+    if (grad) {
+      const double g = __dmul_rn(2.0, diff);
+      double2* g2 = reinterpret_cast<double2*>(grad + 4 * i);
+      g2[0] = make_double2(a == 0 ? g : 0.0, a == 1 ? g : 0.0);
+      g2[1] = make_double2(a == 2 ? g : 0.0, a == 3 ? g : 0.0);
+    }
+    acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+  }
+  const double bs = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = bs;
+    __threadfence();
+    const unsigned int old = atomicInc(ticket, gridDim.x - 1);  // wraps back to 0 for the next launch
+    is_last = (old == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s = __dadd_rn(s, partials[b]);
+    loss[0] = s;
+  }
+}
+
+__global__ void egreedy_kernel(const double* __restrict__ q, const uint8_t* __restrict__ flags,
+                               double eps, uint64_t seed, uint64_t ctr, uint64_t index_base,
+                               const uint8_t* __restrict__ override_bytes,
+                               uint8_t* __restrict__ actions, double* __restrict__ max_q, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ov = override_bytes ? (uint32_t)override_bytes[i] : 0xFFu;
+  bool explore;
+  uint32_t ra;
+  if (ov == 0xFFu) {
+    const uint64_t g = index_base + (uint64_t)i;
+    const uint4 r = philox_at(seed, DOM_EGREEDY, g >> 1, ctr);
+    const uint32_t wu = (g & 1ull) ? r.z : r.x, wa = (g & 1ull) ? r.w : r.y;
+    explore = ((double)wu * (1.0 / 4294967296.0)) < eps;  // np.random.rand() < epsilon
+    ra = wa >> 30;                                        // np.random.randint(4)
+  } else {
+    explore = (ov & 0x80u) == 0;
+    ra = ov & 3u;
+  }
+  if (explore) {
+    actions[i] = (uint8_t)ra;
+    max_q[i] = 0.0;
+    return;
+  }
+  const double2* q2 = reinterpret_cast<const double2*>(q + 4 * i);
+  const double2 qa = q2[0], qb = q2[1];
+  const double qq[4] = {qa.x, qa.y, qb.x, qb.y};
+  const double mn = fmin(fmin(qq[0], qq[1]), fmin(qq[2], qq[3]));
+  const double mx = fmax(fmax(qq[0], qq[1]), fmax(qq[2], qq[3]));
+  const double mm = __dmul_rn(mn, mx);
+  const uint32_t legal = flags[i] & 0xFu;
+  int best = 0;
+  double bv = 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double qn = __dsub_rn(__dsub_rn(qq[j], mm), mn);  // Q - min*max - min, left to right
+    const double v = __dmul_rn(((legal >> j) & 1u) ? 1.0 : 0.0, qn);
+    if (j == 0 || v > bv) { bv = v; best = j; }
+  }
+  actions[i] = (uint8_t)best;
+  max_q[i] = mx;
+}
+
+}  // namespace
+}  // namespace b2048
+
+using namespace b2048;
+
+extern "C" int ddqn_target_loss(const double* q_next_online, const double* q_next_target,
+                                const double* q_cur, const int64_t* actions, const int64_t* rewards,
+                                const int64_t* dones, float gamma_f32, int use_double,
+                                double* target, double* q_sa, double* loss, double* grad_q_cur,
+                                int64_t B, void* stream) {
+  if (B <= 0) return B2048_EINVAL;
+  if (!q_next_target || !q_cur || !actions || !rewards || !dones || !target || !q_sa || !loss)
+    return B2048_EINVAL;
+  if (use_double && !q_next_online) return B2048_EINVAL;
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  int64_t blocks = (B + K3_THREADS - 1) / K3_THREADS;
+  if (blocks > MAX_PARTIALS) blocks = MAX_PARTIALS;
+  ddqn_target_loss_kernel<<<(unsigned)blocks, K3_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      q_next_online, q_next_target, q_cur, actions, rewards, dones, gamma_f32, use_double, target,
+      q_sa, loss, grad_q_cur, B, ctx->partials, ctx->ticket);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int egreedy_select(const double* q, const uint8_t* flags, double eps, uint64_t seed,
+                              uint64_t ctr, uint64_t index_base, const uint8_t* override_bytes,
+                              uint8_t* actions, double* max_q, int64_t n, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!q || !flags || !actions || !max_q) return B2048_EINVAL;
+  int err = 0;
+  if (!current_ctx(&err)) return err;
+  egreedy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, flags, eps, seed, ctr, index_base, override_bytes, actions, max_q, n);
+  return (int)cudaGetLastError();
+}

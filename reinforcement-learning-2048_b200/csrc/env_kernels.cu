@@ -1,0 +1,520 @@
+// env_kernels.cu — K1: batched 2048 environment step on packed u64 boards (sm_100a).
+//
+// Replaces, for n boards per launch, the reference's Board2048.peek_action -> up/down/left/right
+// -> _apply_action_to_vector -> _populate_empty_cell chain (src/board.py:41-51, 92-126, 147-202),
+// the merge-score reward (src/dqn_lib.py:87-88) and the legal-mask / done test
+// (src/board.py:128-135, src/dqn_lib.py:17-18).
+//
+// Streaming kernel (`step_stream_kernel`): persistent, one 1024-thread CTA per SM, the row table
+// staged once per CTA into 224 KB of shared memory with cp.async.bulk (TMA bulk copy, UBLKCP),
+// two boards per thread per iteration through one 128-bit load / store, one Philox4x32-10 call
+// per board pair.  Small batches use `step_small_kernel`, which reads the L2-resident table
+// directly and so skips the 224 KB staging.
+#include "b2048_common.cuh"
+
+namespace b2048 {
+
+namespace {
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Per-board tail shared by both step kernels: flags, changed test, spawn.
+//   w_pos / w_val : the board's two Philox words
+//   ovr           : spawn override byte (B2048_SPAWN_NONE = none)
+__device__ __forceinline__ void finish_board(uint32_t lo, uint32_t hi, uint32_t& nlo, uint32_t& nhi,
+                                             uint32_t overflow, uint32_t w_pos, uint32_t w_val,
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
+  const uint32_t legal = legal_mask(lo, hi);
+  const bool changed = (nlo != lo) | (nhi != hi);
+  flags = legal | (legal ? 0u : B2048_FLAG_DONE) | (changed ? B2048_FLAG_CHANGED : 0u) |
+          (overflow ? B2048_FLAG_OVERFLOW : 0u);
+  if (ovr == B2048_SPAWN_NONE) {
+    uint32_t slo = nlo, shi = nhi;
+    spawn_kth_empty(slo, shi, w_pos, (w_val < p4) ? 2u : 1u);
+    if (changed) {
+      nlo = slo;
+      nhi = shi;
+    }
+  } else if (changed) {
+    if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
+  }
+}
+
+constexpr int STREAM_THREADS = 1024;
+constexpr int STREAM_SMEM_BYTES = LUT_SMEM_BYTES + 4 * 16 + 16;  // table + action xforms + mbarrier
+
+// ---- streaming kernel: two boards per thread, table in shared memory -----------------------------
+// Requires: boards/next 16-byte aligned, actions/flags 2-byte aligned, reward 8-byte aligned,
+// n even (host wrapper peels the odd board / misaligned case into step_small_kernel).
+template <bool HAS_OVERRIDE>
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
+    step_stream_kernel(const uint4* __restrict__ boards2, const uint16_t* __restrict__ actions2,
+                       uint4* __restrict__ next2, uint2* __restrict__ reward2,
+                       uint16_t* __restrict__ flags2, int64_t npairs,
+                       const uint32_t* __restrict__ glut, uint64_t seed, uint64_t step,
+                       uint64_t index_base, uint32_t p4, const uint16_t* __restrict__ override2) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
+  ActXform* sact = reinterpret_cast<ActXform*>(smem_raw + LUT_SMEM_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LUT_SMEM_BYTES + 4 * 16);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 4) sact[threadIdx.x] = act_xform((int)threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
+    constexpr uint32_t CHUNK = 32768;  // 7 bulk copies of 32 KB
+#pragma unroll
+    for (uint32_t off = 0; off < (uint32_t)LUT_SMEM_BYTES; off += CHUNK)
+      bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut) + off, CHUNK, bar);
+  }
+
+  const int64_t stride = (int64_t)gridDim.x * STREAM_THREADS;
+  int64_t pair = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+  const bool base_odd = (index_base & 1ull) != 0;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ DOM_SPAWN;
+  const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
+
+  // first loads are issued before waiting for the table
+  uint4 b = make_uint4(0, 0, 0, 0);
+  uint32_t a2 = 0, o2 = 0xFFFFu;
+  if (pair < npairs) {
+    b = ld_stream_v4(boards2 + pair);
+    a2 = actions2[pair];
+    if (HAS_OVERRIDE) o2 = override2[pair];
+  }
+  mbar_wait(bar, 0);
+
+  while (pair < npairs) {
+    // prefetch the next pair of this thread
+    const int64_t nxt = pair + stride;
+    uint4 bn = make_uint4(0, 0, 0, 0);
+    uint32_t an = 0, on = 0xFFFFu;
+    if (nxt < npairs) {
+      bn = ld_stream_v4(boards2 + nxt);
+      an = actions2[nxt];
+      if (HAS_OVERRIDE) on = override2[nxt];
+    }
+
+    // Philox: one call per aligned global pair; words (x,y) -> even board, (z,w) -> odd board
+    const uint64_t g0 = index_base + 2ull * (uint64_t)pair;
+    uint32_t wp0, wv0, wp1, wv1;
+    {
+      const uint64_t pidx = g0 >> 1;
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi),
+                                    k0, k1);
+      if (!base_odd) {
+        wp0 = r.x; wv0 = r.y; wp1 = r.z; wv1 = r.w;
+      } else {
+        const uint64_t pidx1 = pidx + 1;
+        const uint4 r1 = philox4x32_10(
+            make_uint4((uint32_t)pidx1, (uint32_t)(pidx1 >> 32), s_lo, s_hi), k0, k1);
+        wp0 = r.z; wv0 = r.w; wp1 = r1.x; wv1 = r1.y;
+      }
+    }
+
+    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, ov0, ov1, f0, f1;
+    slide_board<true>(b.x, b.y, sact[a2 & 3u], slut, glut, n0l, n0h, rw0, ov0);
+    slide_board<true>(b.z, b.w, sact[(a2 >> 8) & 3u], slut, glut, n1l, n1h, rw1, ov1);
+    finish_board(b.x, b.y, n0l, n0h, ov0, wp0, wv0, p4, HAS_OVERRIDE ? (o2 & 0xFFu) : 0xFFu, f0);
+    finish_board(b.z, b.w, n1l, n1h, ov1, wp1, wv1, p4, HAS_OVERRIDE ? (o2 >> 8) : 0xFFu, f1);
+
+    st_stream_v4(next2 + pair, make_uint4(n0l, n0h, n1l, n1h));
+    st_stream_v2(reward2 + pair, make_uint2(rw0, rw1));
+    flags2[pair] = (uint16_t)(f0 | (f1 << 8));
+
+    b = bn; a2 = an; o2 = on;
+    pair = nxt;
+  }
+}
+
+// ---- small-batch / unaligned kernel: one board per thread, table from global (L2) ---------------
+template <bool HAS_OVERRIDE>
+__global__ void __launch_bounds__(256)
+    step_small_kernel(const uint64_t* __restrict__ boards, const uint8_t* __restrict__ actions,
+                      uint64_t* __restrict__ next, int32_t* __restrict__ reward,
+                      uint8_t* __restrict__ flags, int64_t n, const uint32_t* __restrict__ glut,
+                      uint64_t seed, uint64_t step, uint64_t index_base, uint32_t p4,
+                      const uint8_t* __restrict__ override1) {
+  __shared__ ActXform sact[4];
+  if (threadIdx.x < 4) sact[threadIdx.x] = act_xform((int)threadIdx.x);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t bd = boards[i];
+  const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
+  const uint64_t g = index_base + (uint64_t)i;
+  const uint4 r = philox_at(seed, DOM_SPAWN, g >> 1, step);
+  const uint32_t wp = (g & 1ull) ? r.z : r.x, wv = (g & 1ull) ? r.w : r.y;
+  uint32_t nl, nh, rw, ov, f;
+  slide_board<false>(lo, hi, sact[actions[i] & 3u], nullptr, glut, nl, nh, rw, ov);
+  finish_board(lo, hi, nl, nh, ov, wp, wv, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
+  next[i] = ((uint64_t)nh << 32) | nl;
+  reward[i] = (int32_t)rw;
+  flags[i] = (uint8_t)f;
+}
+
+// ---- all four actions per board (BASELINE.json config 2) ------------------------------------------
+template <bool SMEM, bool HAS_OVERRIDE>
+__device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const uint32_t* slut,
+                                           const uint32_t* __restrict__ glut, uint32_t wp,
+                                           uint32_t wv, uint32_t p4, uint32_t ovr4, uint32_t nl[4],
+                                           uint32_t nh[4], uint32_t rw[4], uint32_t& flags) {
+  uint32_t legal = 0, ovf = 0, bad = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    uint32_t ov;
+    slide_board<SMEM>(lo, hi, act_xform(a), slut, glut, nl[a], nh[a], rw[a], ov);
+    ovf |= ov;
+    const bool changed = (nl[a] != lo) | (nh[a] != hi);
+    legal |= changed ? (1u << a) : 0u;
+    const uint32_t ovr = HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu;
+    if (ovr == B2048_SPAWN_NONE) {
+      uint32_t sl = nl[a], sh = nh[a];
+      spawn_kth_empty(sl, sh, wp, (wv < p4) ? 2u : 1u);
+      if (changed) { nl[a] = sl; nh[a] = sh; }
+    } else if (changed) {
+      if (!spawn_at(nl[a], nh[a], ovr & 0xFu, (ovr >> 4) & 0xFu)) bad = B2048_FLAG_BADSPAWN;
+    }
+  }
+  flags = legal | (legal ? 0u : B2048_FLAG_DONE) | (ovf ? B2048_FLAG_OVERFLOW : 0u) | bad;
+}
+
+template <bool HAS_OVERRIDE>
+__global__ void __launch_bounds__(256)
+    step_all4_kernel(const uint64_t* __restrict__ boards, uint4* __restrict__ next4,
+                     uint4* __restrict__ reward4, uint8_t* __restrict__ flags, int64_t n,
+                     const uint32_t* __restrict__ glut, uint64_t seed, uint64_t step,
+                     uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t bd = boards[i];
+  const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
+  const uint64_t g = index_base + (uint64_t)i;
+  const uint4 r = philox_at(seed, DOM_SPAWN, g >> 1, step);
+  const uint32_t wp = (g & 1ull) ? r.z : r.x, wv = (g & 1ull) ? r.w : r.y;
+  uint32_t nl[4], nh[4], rw[4], f;
+  all4_board<false, HAS_OVERRIDE>(lo, hi, nullptr, glut, wp, wv, p4,
+                                  HAS_OVERRIDE ? override4[i] : 0xFFFFFFFFu, nl, nh, rw, f);
+  st_stream_v4(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]));
+  st_stream_v4(next4 + 2 * i + 1, make_uint4(nl[2], nh[2], nl[3], nh[3]));
+  st_stream_v4(reward4 + i, make_uint4(rw[0], rw[1], rw[2], rw[3]));
+  flags[i] = (uint8_t)f;
+}
+
+// ---- helpers: legal mask, reset, pack/unpack, synthetic inputs ---------------------------------
+__global__ void legal_mask_kernel(const uint64_t* __restrict__ boards, uint8_t* __restrict__ flags,
+                                  int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t bd = boards[i];
+  const uint32_t m = legal_mask((uint32_t)bd, (uint32_t)(bd >> 32));
+  flags[i] = (uint8_t)(m | (m ? 0u : B2048_FLAG_DONE));
+}
+
+__global__ void reset_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t seed, uint64_t step,
+                             uint64_t index_base, uint32_t p4,
+                             const uint8_t* __restrict__ where_flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (where_flags && !(where_flags[i] & B2048_FLAG_DONE)) return;
+  const uint4 r = philox_at(seed, DOM_RESET, index_base + (uint64_t)i, step);
+  // first spawn: uniform over 16 cells; second: uniform over the remaining 15 (row-major rank)
+  const uint32_t c1 = r.x >> 28;
+  const uint32_t e1 = (r.y < p4) ? 2u : 1u;
+  uint32_t lo = 0, hi = 0;
+  spawn_at(lo, hi, c1, e1);
+  spawn_kth_empty(lo, hi, r.z, (r.w < p4) ? 2u : 1u);
+  boards[i] = ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void pack_kernel(const int64_t* __restrict__ tiles, uint64_t* __restrict__ boards,
+                            uint8_t* __restrict__ bad, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t b = 0;
+  bool is_bad = false;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int64_t t = tiles[i * 16 + c];
+    uint32_t e = 0;
+    if (t != 0) {
+      if (t < 2 || t > 32768 || (t & (t - 1)) != 0) {
+        is_bad = true;
+      } else {
+        e = 63u - (uint32_t)__clzll(t);
+      }
+    }
+    b |= (uint64_t)e << (4 * c);
+  }
+  boards[i] = b;
+  if (bad) bad[i] = is_bad ? 1 : 0;
+}
+
+__global__ void unpack_tiles_kernel(const uint64_t* __restrict__ boards, int64_t* __restrict__ tiles,
+                                    int64_t n16) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per cell
+  if (j >= n16) return;
+  const uint32_t e = (uint32_t)(boards[j >> 4] >> (4 * (j & 15))) & 0xFu;
+  tiles[j] = e ? ((int64_t)1 << e) : 0;
+}
+
+__global__ void unpack_f64_kernel(const uint64_t* __restrict__ boards, double* __restrict__ out,
+                                  int64_t n16) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n16) return;
+  out[j] = (double)((uint32_t)(boards[j >> 4] >> (4 * (j & 15))) & 0xFu);
+}
+
+__global__ void random_boards_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t seed,
+                                     uint64_t index_base, uint32_t p_empty, uint32_t max_exp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t g = index_base + (uint64_t)i;
+  uint64_t b = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {  // 8 Philox calls -> 32 words -> 16 cells x (empty?, exponent)
+    const uint4 r = philox_at(seed, DOM_BOARDS, g, (uint64_t)q);
+    const uint32_t e0 = (r.x < p_empty) ? 0u : 1u + __umulhi(r.y, max_exp);
+    const uint32_t e1 = (r.z < p_empty) ? 0u : 1u + __umulhi(r.w, max_exp);
+    b |= (uint64_t)e0 << (8 * q);
+    b |= (uint64_t)e1 << (8 * q + 4);
+  }
+  boards[i] = b;
+}
+
+__global__ void random_actions_kernel(uint8_t* __restrict__ actions, int64_t n, uint64_t seed,
+                                      uint64_t step, uint64_t index_base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t g = index_base + (uint64_t)i;
+  const uint4 r = philox_at(seed, DOM_ACTIONS, g >> 2, step);
+  const uint32_t w = (g & 2ull) ? ((g & 1ull) ? r.w : r.z) : ((g & 1ull) ? r.y : r.x);
+  actions[i] = (uint8_t)(w >> 30);
+}
+
+inline int64_t blocks_for(int64_t n, int threads) { return (n + threads - 1) / threads; }
+
+// Batches at or above this many boards use the persistent shared-memory-table kernel.
+constexpr int64_t STREAM_MIN_BOARDS = 1 << 19;
+
+template <bool HAS_OVERRIDE>
+cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint8_t* actions,
+                        uint64_t* next, int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed,
+                        uint64_t step, uint64_t index_base, uint32_t p4, const uint8_t* ovr,
+                        cudaStream_t st) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next)) & 15u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(reward) & 7u) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(flags) |
+                         reinterpret_cast<uintptr_t>(ovr)) & 1u) == 0;
+  int64_t done = 0;
+  if (aligned && n >= STREAM_MIN_BOARDS) {
+    const int64_t npairs = n / 2;
+    step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
+        reinterpret_cast<const uint4*>(boards), reinterpret_cast<const uint16_t*>(actions),
+        reinterpret_cast<uint4*>(next), reinterpret_cast<uint2*>(reward),
+        reinterpret_cast<uint16_t*>(flags), npairs, ctx->lut, seed, step, index_base, p4,
+        reinterpret_cast<const uint16_t*>(ovr));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    done = npairs * 2;
+  }
+  if (done < n) {
+    const int64_t m = n - done;
+    step_small_kernel<HAS_OVERRIDE><<<(unsigned)blocks_for(m, 256), 256, 0, st>>>(
+        boards + done, actions + done, next + done, reward + done, flags + done, m, ctx->lut, seed,
+        step, index_base + (uint64_t)done, p4, HAS_OVERRIDE ? ovr + done : nullptr);
+    return cudaGetLastError();
+  }
+  return cudaSuccess;
+}
+
+}  // namespace
+
+// one-time kernel attribute setup (called from b2048_init)
+cudaError_t env_kernels_configure() {
+  cudaError_t e = cudaFuncSetAttribute(step_stream_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(step_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              STREAM_SMEM_BYTES);
+}
+
+}  // namespace b2048
+
+using namespace b2048;
+
+#define B2048_CTX_OR_RETURN()            \
+  int ctx_err__ = 0;                     \
+  DeviceCtx* ctx = current_ctx(&ctx_err__); \
+  if (!ctx) return ctx_err__;
+
+extern "C" int b2048_step(const uint64_t* boards, const uint8_t* actions, uint64_t* next,
+                          int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed, uint64_t step,
+                          uint64_t index_base, uint32_t p4_threshold, const uint8_t* spawn_override,
+                          void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!boards || !actions || !next || !reward || !flags) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return spawn_override
+             ? (int)launch_step<true>(ctx, boards, actions, next, reward, flags, n, seed, step,
+                                      index_base, p4_threshold, spawn_override, st)
+             : (int)launch_step<false>(ctx, boards, actions, next, reward, flags, n, seed, step,
+                                       index_base, p4_threshold, nullptr, st);
+}
+
+extern "C" int b2048_step_all4(const uint64_t* boards, uint64_t* next4, int32_t* reward4,
+                               uint8_t* flags, int64_t n, uint64_t seed, uint64_t step,
+                               uint64_t index_base, uint32_t p4_threshold,
+                               const uint8_t* spawn_override4, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!boards || !next4 || !reward4 || !flags) return B2048_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(next4) | reinterpret_cast<uintptr_t>(reward4)) & 15u) return B2048_EINVAL;
+  if (reinterpret_cast<uintptr_t>(spawn_override4) & 3u) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)blocks_for(n, 256);
+  if (spawn_override4)
+    step_all4_kernel<true><<<grid, 256, 0, st>>>(boards, reinterpret_cast<uint4*>(next4),
+                                                 reinterpret_cast<uint4*>(reward4), flags, n, ctx->lut,
+                                                 seed, step, index_base, p4_threshold,
+                                                 reinterpret_cast<const uint32_t*>(spawn_override4));
+  else
+    step_all4_kernel<false><<<grid, 256, 0, st>>>(boards, reinterpret_cast<uint4*>(next4),
+                                                  reinterpret_cast<uint4*>(reward4), flags, n, ctx->lut,
+                                                  seed, step, index_base, p4_threshold, nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_legal_mask(const uint64_t* boards, uint8_t* flags, int64_t n, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!boards || !flags) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  legal_mask_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, flags, n);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_reset(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step,
+                           uint64_t index_base, uint32_t p4_threshold, const uint8_t* where_flags,
+                           void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!boards) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  reset_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, n, seed, step, index_base, p4_threshold, where_flags);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_pack(const int64_t* tiles, uint64_t* boards, uint8_t* bad, int64_t n,
+                          void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!tiles || !boards) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  pack_kernel<<<(unsigned)blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      tiles, boards, bad, n);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_unpack_tiles(const uint64_t* boards, int64_t* tiles, int64_t n, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!tiles || !boards) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  unpack_tiles_kernel<<<(unsigned)blocks_for(n * 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, tiles, n * 16);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_unpack_f64(const uint64_t* boards, double* out, int64_t n, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!out || !boards) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  unpack_f64_kernel<<<(unsigned)blocks_for(n * 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, out, n * 16);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_random_boards(uint64_t* boards, int64_t n, uint64_t seed, uint64_t index_base,
+                                   uint32_t p_empty_threshold, uint32_t max_exp, void* stream) {
+  if (n < 0 || max_exp < 1 || max_exp > 15) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!boards) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  random_boards_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, n, seed, index_base, p_empty_threshold, max_exp);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_random_actions(uint8_t* actions, int64_t n, uint64_t seed, uint64_t step,
+                                    uint64_t index_base, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!actions) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  random_actions_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      actions, n, seed, step, index_base);
+  return (int)cudaGetLastError();
+}
+
+// used by host_api.cu (b2048_step_host)
+namespace b2048 {
+int step_device(DeviceCtx* ctx, const uint64_t* boards, const uint8_t* actions, uint64_t* next,
+                int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed, uint64_t step,
+                uint64_t index_base, uint32_t p4, const uint8_t* ovr, cudaStream_t st) {
+  return ovr ? (int)launch_step<true>(ctx, boards, actions, next, reward, flags, n, seed, step,
+                                      index_base, p4, ovr, st)
+             : (int)launch_step<false>(ctx, boards, actions, next, reward, flags, n, seed, step,
+                                       index_base, p4, nullptr, st);
+}
+}  // namespace b2048
