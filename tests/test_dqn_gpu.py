@@ -173,5 +173,5 @@ def test_egreedy_matches_reference(cuda, golden_dir):
     explored = (mqm == 0) & (qb.max(dim=1).values != 0)
     assert 0.29 < explored.float().mean().item() < 0.31
     ao, mo = do.egreedy_batch(qb.cpu().numpy()[:2000], fb.cpu().numpy()[:2000], np.full(2000, 0x80, np.uint8))
-    keep = ~explored[:2000].cpu().numpy()
+    keep = (~explored & (qb.max(dim=1).values != 0))[:2000].cpu().numpy()
     assert np.array_equal(actm.cpu().numpy()[:2000][keep], ao[keep])
