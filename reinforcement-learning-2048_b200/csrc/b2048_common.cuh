@@ -48,19 +48,54 @@ DeviceCtx* current_ctx(int* err);
 DeviceCtx* ctx_for(int device);
 
 // ---- Philox4x32-10 (Salmon et al., SC'11; same constants as Random123 / cuRAND) -----------------
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  // one IMAD.WIDE; the plain C++ 64-bit product makes nvcc add a spurious zero to the high word
+  asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+  const uint64_t p = (uint64_t)a * b;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+#endif
+}
+
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
-    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
-    const uint32_t nx = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
-    const uint32_t nz = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
-    c.y = (uint32_t)p1;
-    c.w = (uint32_t)p0;
-    c.x = nx;
-    c.z = nz;
+    uint32_t h0, l0, h1, l1;
+    mulhilo32(0xD2511F53u, c.x, h0, l0);
+    mulhilo32(0xCD9E8D57u, c.z, h1, l1);
+    c = make_uint4(h1 ^ c.y ^ k0, l1, h0 ^ c.w ^ k1, l0);
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// The ten round keys of one seed, computed once on the host and passed by value as a kernel
+// argument: they then sit in the constant bank and feed the round XORs directly, instead of
+// being re-derived with 20 integer adds per call inside the ALU-bound loop.
+struct PhiloxKeys {
+  uint32_t k[20];
+};
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed, uint32_t domain) {
+  PhiloxKeys pk;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ domain;
+  for (int i = 0; i < 10; ++i) {
+    pk.k[2 * i] = k0;
+    pk.k[2 * i + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return pk;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& pk) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t h0, l0, h1, l1;
+    mulhilo32(0xD2511F53u, c.x, h0, l0);
+    mulhilo32(0xCD9E8D57u, c.z, h1, l1);
+    c = make_uint4(h1 ^ c.y ^ pk.k[2 * i], l1, h0 ^ c.w ^ pk.k[2 * i + 1], l0);
   }
   return c;
 }
@@ -73,9 +108,20 @@ __host__ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t doma
 }
 
 // ---- nibble SWAR ------------------------------------------------------------------------------
+// The step kernel is bound by the SM's integer ALU pipe (LOP3/SHF/PRMT/ISETP/SEL: one warp
+// instruction per 2 cycles per sub-partition, measured in profiles/ubench), not by HBM.  Where an
+// operation has an equivalent on the FMA pipe it is written that way on purpose:
+//   x >> k  ->  __umulhi(x, 1 << (32-k))   (IMAD.HI)      x << k -> x * (1 << k)  (IMAD.SHL)
+//   a | b with disjoint bits -> a + b / a * m + b          (IMAD)
+__device__ __forceinline__ uint32_t shr_fma(uint32_t v, int k) { return __umulhi(v, 1u << (32 - k)); }
+
 // bit 3 of every nibble set iff the nibble is non-zero (carry-free: 7+7 < 16).
 __device__ __forceinline__ uint32_t nz3(uint32_t v) {
   return (((v & 0x77777777u) + 0x77777777u) | v) & 0x88888888u;
+}
+// same for a ^ b, WITHOUT the final mask (bits other than bit 3 of each nibble are garbage)
+__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b) {
+  return (((a ^ b) & 0x77777777u) + 0x77777777u) | (a ^ b);
 }
 
 // Legal-move mask (bits: up, down, left, right) of a board, without the row table: a move toward
@@ -107,86 +153,161 @@ __device__ __forceinline__ uint32_t legal_mask(uint32_t lo, uint32_t hi) {
 // is the nibble part of the 4x4 transpose (s = 12, m = 0x0000F0F0) or the nibble swap inside each
 // byte of a horizontal flip (s = 4, m = 0x0F0F0F0F); for `left` m = 0.  Both halves are
 // involutions, so the inverse is delta-swap first, then the inverse byte permutation.
+// The shifts are stored as multipliers (mul_l = 2^s, mul_r = 2^(32-s)) so that they run on the
+// FMA pipe (IMAD / IMAD.HI) instead of the ALU pipe.
 struct ActXform {
   uint32_t sel_fwd;  // lo selector | hi selector << 16
   uint32_t sel_inv;
-  uint32_t shift;
+  uint32_t mul_l;    // 1 << s
+  uint32_t mul_r;    // 1 << (32 - s)
   uint32_t mask;
+  uint32_t pad0, pad1, pad2;
 };
 
 __host__ __device__ constexpr ActXform act_xform(int a) {
-  return a == 0   ? ActXform{0x6240u | (0x7351u << 16), 0x6240u | (0x7351u << 16), 12u, 0x0000F0F0u}
-         : a == 1 ? ActXform{0x0426u | (0x1537u << 16), 0x5173u | (0x4062u << 16), 12u, 0x0000F0F0u}
-         : a == 2 ? ActXform{0x3210u | (0x7654u << 16), 0x3210u | (0x7654u << 16), 0u, 0u}
-                  : ActXform{0x2301u | (0x6745u << 16), 0x2301u | (0x6745u << 16), 4u, 0x0F0F0F0Fu};
+  return a == 0   ? ActXform{0x6240u | (0x7351u << 16), 0x6240u | (0x7351u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 0, 0, 0}
+         : a == 1 ? ActXform{0x0426u | (0x1537u << 16), 0x5173u | (0x4062u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 0, 0, 0}
+         : a == 2 ? ActXform{0x3210u | (0x7654u << 16), 0x3210u | (0x7654u << 16), 1u << 4, 1u << 28, 0u, 0, 0, 0}
+                  : ActXform{0x2301u | (0x6745u << 16), 0x2301u | (0x6745u << 16), 1u << 4, 1u << 28, 0x0F0F0F0Fu, 0, 0, 0};
 }
 
-__device__ __forceinline__ uint32_t delta_swap(uint32_t v, uint32_t s, uint32_t m) {
-  const uint32_t t = (v ^ (v >> s)) & m;
-  return v ^ t ^ (t << s);
+__device__ __forceinline__ uint32_t delta_swap(uint32_t v, const ActXform& x) {
+  const uint32_t t = (v ^ __umulhi(v, x.mul_r)) & x.mask;
+  return v ^ t ^ (t * x.mul_l);
 }
 
-// Look one transformed row up.  `slut` may be the shared-memory copy (first LUT_SMEM_ROWS rows)
-// or NULL, in which case every lookup goes to the global table.
+// Legal-mask byte for (action a, transformed-frame mask m): m bit0 = rows can slide left (= the
+// move changes the board), bit1 = right, bit2 = toward row 0, bit3 = toward row 3 of the
+// TRANSFORMED board; the table maps them back to [up, down, left, right] of the real board and
+// adds B2048_FLAG_DONE when nothing is legal.
+__host__ __device__ constexpr uint32_t zframe_to_legal(int a, uint32_t m) {
+  const uint32_t b0 = m & 1u, b1 = (m >> 1) & 1u, b2 = (m >> 2) & 1u, b3 = (m >> 3) & 1u;
+  const uint32_t legal = a == 0   ? (b0 | b1 << 1 | b2 << 2 | b3 << 3)    // z = T(x): left=up, right=down, rows<->cols
+                         : a == 1 ? (b1 | b0 << 1 | b2 << 2 | b3 << 3)    // z = T(flipV(x)): left=down, right=up
+                         : a == 2 ? (b2 | b3 << 1 | b0 << 2 | b1 << 3)    // z = x
+                                  : (b2 | b3 << 1 | b1 << 2 | b0 << 3);   // z = flipH(x): left=right
+  return legal | (legal ? 0u : (uint32_t)B2048_FLAG_DONE);
+}
+
+// per-CTA constant tables in shared memory
+struct SmemTabs {
+  ActXform act[4];        // 128 B
+  uint8_t legal[4][16];   //  64 B
+};
+
+__device__ __forceinline__ void fill_tabs(SmemTabs* t) {
+  if (threadIdx.x < 4) t->act[threadIdx.x] = act_xform((int)threadIdx.x);
+  if (threadIdx.x < 64) t->legal[threadIdx.x >> 4][threadIdx.x & 15] =
+      (uint8_t)zframe_to_legal((int)(threadIdx.x >> 4), threadIdx.x & 15u);
+}
+
+// Row-table entry (host_api.cu builds it):
+//   bits  0-15 result row            bits 16-29 merge reward / 4
+//   bit  30    the row can move RIGHT (toward nibble 3)      bit 31 overflow (32768+32768)
+// Row 0xEEEE (reward/4 = 0x4000) does not fit 14 bits; it is never in the shared-memory part
+// (top nibble 14) and the global path adds its 65536 separately.
+constexpr uint32_t ENTRY_RIGHT = 0x40000000u, ENTRY_OVF = 0x80000000u;
+
+// Look the four transformed rows up.  Fast path: all four rows are in the shared-memory part of
+// the table (checked once per board with a packed 16-bit max); otherwise all four go to the
+// global table (rare: a 16384/32768 tile in the last position of a transformed row).
+__device__ __forceinline__ uint32_t lut_at(const uint32_t* base, uint32_t byte_off) {
+  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(base) + byte_off);
+}
+static __device__ __noinline__ void lookup4_global(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut,
+                                            uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3,
+                                            uint32_t& extra) {
+  const uint32_t i0 = zl & 0xFFFFu, i1 = zl >> 16, i2 = zh & 0xFFFFu, i3 = zh >> 16;
+  e0 = __ldg(glut + i0);
+  e1 = __ldg(glut + i1);
+  e2 = __ldg(glut + i2);
+  e3 = __ldg(glut + i3);
+  extra = ((i0 == 0xEEEEu) + (i1 == 0xEEEEu) + (i2 == 0xEEEEu) + (i3 == 0xEEEEu)) * 65536u;
+}
 template <bool SMEM>
-__device__ __forceinline__ uint32_t row_lookup(uint32_t idx, const uint32_t* slut,
-                                               const uint32_t* __restrict__ glut) {
+__device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t* slut,
+                                        const uint32_t* __restrict__ glut, uint32_t& e0, uint32_t& e1,
+                                        uint32_t& e2, uint32_t& e3, uint32_t& extra) {
   if (SMEM) {
-    if (idx < (uint32_t)LUT_SMEM_ROWS) return slut[idx];
-    return __ldg(glut + idx);
+    const uint32_t mx = __vmaxu2(zl, zh);
+    if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
+      lookup4_global(zl, zh, glut, e0, e1, e2, e3, extra);
+    } else {
+      e0 = lut_at(slut, (zl * 4u) & 0x3FFFCu);
+      e1 = lut_at(slut, shr_fma(zl, 14) & 0x3FFFCu);
+      e2 = lut_at(slut, (zh * 4u) & 0x3FFFCu);
+      e3 = lut_at(slut, shr_fma(zh, 14) & 0x3FFFCu);
+      extra = 0;
+    }
   } else {
-    return __ldg(glut + idx);
+    lookup4_global(zl, zh, glut, e0, e1, e2, e3, extra);
   }
 }
 
-// Slide + merge one board by one action.  Outputs the slid board (no spawn), merge reward and
-// overflow flag (0 or non-zero).
+// Slide + merge one board by one action, and derive the legal mask of the INPUT board in the
+// transformed frame.  Outputs: slid board (no spawn), reward, flags (legal | done | changed |
+// overflow).
 template <bool SMEM>
-__device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, const ActXform x,
+__device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a, const SmemTabs* tabs,
                                             const uint32_t* slut, const uint32_t* __restrict__ glut,
                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward,
-                                            uint32_t& overflow) {
+                                            uint32_t& flags, uint32_t& changed) {
+  const ActXform x = tabs->act[a];
   uint32_t zl = __byte_perm(lo, hi, x.sel_fwd);
-  uint32_t zh = __byte_perm(lo, hi, x.sel_fwd >> 16);
-  zl = delta_swap(zl, x.shift, x.mask);
-  zh = delta_swap(zh, x.shift, x.mask);
-  const uint32_t e0 = row_lookup<SMEM>(zl & 0xFFFFu, slut, glut);
-  const uint32_t e1 = row_lookup<SMEM>(zl >> 16, slut, glut);
-  const uint32_t e2 = row_lookup<SMEM>(zh & 0xFFFFu, slut, glut);
-  const uint32_t e3 = row_lookup<SMEM>(zh >> 16, slut, glut);
-  uint32_t wl = __byte_perm(e0, e1, 0x5410);
-  uint32_t wh = __byte_perm(e2, e3, 0x5410);
+  uint32_t zh = __byte_perm(lo, hi, shr_fma(x.sel_fwd, 16));
+  zl = delta_swap(zl, x);
+  zh = delta_swap(zh, x);
+  uint32_t e0, e1, e2, e3, extra;
+  lookup4<SMEM>(zl, zh, slut, glut, e0, e1, e2, e3, extra);
+  uint32_t wl = (e0 & 0xFFFFu) + (e1 << 16);
+  uint32_t wh = (e2 & 0xFFFFu) + (e3 << 16);
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
-  overflow = (h01 | h23) & 0x80008000u;
-  const uint32_t s = (h01 & 0x7FFF7FFFu) + (h23 & 0x7FFF7FFFu);  // two 16-bit lanes, no carry
-  reward = ((s & 0xFFFFu) + (s >> 16)) << 2;
-  wl = delta_swap(wl, x.shift, x.mask);
-  wh = delta_swap(wh, x.shift, x.mask);
+  const uint32_t fl = h01 | h23;
+  // two 16-bit lanes of reward/4 (each <= 2 * 0x3000), summed and scaled by 4 with one dp2a
+  const uint32_t s = (h01 & 0x3FFF3FFFu) + (h23 & 0x3FFF3FFFu);
+  reward = __dp2a_lo(s, 0x0404u, extra);
+
+  // transformed-frame legality: left = changed, right = any row's RIGHT bit, and the
+  // perpendicular axis by SWAR on z: pair (row r, row r+1) sits at row r.
+  changed = (wl ^ zl) | (wh ^ zh);
+  const uint32_t n_l = nz3(zl), n_h = nz3(zh);
+  const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = shr_fma(zh, 16);
+  const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
+  const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = shr_fma(n_h, 16);
+  const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
+  const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
+  const uint32_t m = (changed ? 1u : 0u) | ((fl & 0x40004000u) ? 2u : 0u) | (up ? 4u : 0u) |
+                     ((dn_l | (dn_h & 0x0000FFFFu)) ? 8u : 0u);
+  flags = tabs->legal[a][m] | (changed ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
+          ((fl & 0x80008000u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u);
+
+  wl = delta_swap(wl, x);
+  wh = delta_swap(wh, x);
   olo = __byte_perm(wl, wh, x.sel_inv);
-  ohi = __byte_perm(wl, wh, x.sel_inv >> 16);
+  ohi = __byte_perm(wl, wh, shr_fma(x.sel_inv, 16));
 }
 
 // ---- spawn ---------------------------------------------------------------------------------------
-// Put exponent `e` into the k-th empty cell (row-major) where k = floor(w_pos * n_empty / 2^32).
-// Requires at least one empty cell and at most 15 (true after any board-changing move).
+// Put exponent `e` (0 = nothing) into the k-th empty cell (row-major) where
+// k = floor(w_pos * n_empty / 2^32).  Requires at most 15 empty cells.
 __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint32_t w_pos,
                                                 uint32_t e) {
-  const uint32_t e_lo = (~nz3(lo) & 0x88888888u) >> 3;  // bit 0 of every empty nibble
-  const uint32_t e_hi = (~nz3(hi) & 0x88888888u) >> 3;
+  const uint32_t e3_lo = ~(((lo & 0x77777777u) + 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
+  const uint32_t e3_hi = ~(((hi & 0x77777777u) + 0x77777777u) | hi) & 0x88888888u;
+  const uint32_t e_lo = shr_fma(e3_lo, 3), e_hi = shr_fma(e3_hi, 3);
   // inclusive prefix counts per nibble: multiply by 0x11111111 (counts <= 15 never carry)
   const uint32_t p_lo = e_lo * 0x11111111u;
-  const uint32_t c_lo = p_lo >> 28;
-  const uint32_t p_hi = (e_hi + c_lo) * 0x11111111u;
-  const uint32_t cnt = p_hi >> 28;
-  const uint32_t k1 = __umulhi(w_pos, cnt) + 1u;  // 1-based rank of the chosen empty cell
-  const uint32_t tgt = k1 * 0x11111111u;
-  // the chosen nibble is the empty one whose prefix count equals k1
-  const uint32_t h_lo = ~nz3(p_lo ^ tgt) & (e_lo << 3);
-  const uint32_t h_hi = ~nz3(p_hi ^ tgt) & (e_hi << 3);
-  // exactly one bit (bit 3 of the chosen nibble) is set across h_lo/h_hi
-  lo |= (h_lo >> 3) * e;
-  hi |= (h_hi >> 3) * e;
+  const uint32_t c_lo = shr_fma(p_lo, 28);
+  const uint32_t p_hi = e_hi * 0x11111111u + c_lo * 0x11111111u;
+  const uint32_t cnt = shr_fma(p_hi, 28);
+  const uint32_t tgt = __umulhi(w_pos, cnt) * 0x11111111u + 0x11111111u;  // (k+1) in every nibble
+  // the chosen nibble is the empty one whose prefix count equals k+1
+  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt) & e3_lo;
+  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt) & e3_hi;
+  // exactly one bit (bit 3 of the chosen nibble) is set across h_lo/h_hi; the cell is empty so + == |
+  lo += shr_fma(h_lo, 3) * e;
+  hi += shr_fma(h_hi, 3) * e;
 }
 
 // Insert exponent e at cell (0..15); returns false if the cell is occupied.

@@ -51,30 +51,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
-// Per-board tail shared by both step kernels: flags, changed test, spawn.
+// Per-board tail shared by both step kernels: spawn one tile iff the move changed the board.
 //   w_pos / w_val : the board's two Philox words
 //   ovr           : spawn override byte (B2048_SPAWN_NONE = none)
-__device__ __forceinline__ void finish_board(uint32_t lo, uint32_t hi, uint32_t& nlo, uint32_t& nhi,
-                                             uint32_t overflow, uint32_t w_pos, uint32_t w_val,
-                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
-  const uint32_t legal = legal_mask(lo, hi);
-  const bool changed = (nlo != lo) | (nhi != hi);
-  flags = legal | (legal ? 0u : B2048_FLAG_DONE) | (changed ? B2048_FLAG_CHANGED : 0u) |
-          (overflow ? B2048_FLAG_OVERFLOW : 0u);
-  if (ovr == B2048_SPAWN_NONE) {
-    uint32_t slo = nlo, shi = nhi;
-    spawn_kth_empty(slo, shi, w_pos, (w_val < p4) ? 2u : 1u);
-    if (changed) {
-      nlo = slo;
-      nhi = shi;
-    }
+template <bool HAS_OVERRIDE>
+__device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w_pos,
+                                             uint32_t w_val, uint32_t p4, uint32_t ovr, uint32_t& flags) {
+  const uint32_t e = changed ? ((w_val < p4) ? 2u : 1u) : 0u;
+  if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
+    spawn_kth_empty(nlo, nhi, w_pos, e);
   } else if (changed) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
 }
 
 constexpr int STREAM_THREADS = 1024;
-constexpr int STREAM_SMEM_BYTES = LUT_SMEM_BYTES + 4 * 16 + 16;  // table + action xforms + mbarrier
+constexpr int STREAM_SMEM_BYTES = LUT_SMEM_BYTES + (int)sizeof(SmemTabs) + 16;  // row table + small tables + mbarrier
 
 // ---- streaming kernel: two boards per thread, table in shared memory -----------------------------
 // Requires: boards/next 16-byte aligned, actions/flags 2-byte aligned, reward 8-byte aligned,
@@ -84,18 +76,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     step_stream_kernel(const uint4* __restrict__ boards2, const uint16_t* __restrict__ actions2,
                        uint4* __restrict__ next2, uint2* __restrict__ reward2,
                        uint16_t* __restrict__ flags2, int64_t npairs,
-                       const uint32_t* __restrict__ glut, uint64_t seed, uint64_t step,
+                       const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
                        uint64_t index_base, uint32_t p4, const uint16_t* __restrict__ override2) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
-  ActXform* sact = reinterpret_cast<ActXform*>(smem_raw + LUT_SMEM_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LUT_SMEM_BYTES + 4 * 16);
+  SmemTabs* tabs = reinterpret_cast<SmemTabs*>(smem_raw + LUT_SMEM_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LUT_SMEM_BYTES + sizeof(SmemTabs));
 
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 4) sact[threadIdx.x] = act_xform((int)threadIdx.x);
+  fill_tabs(tabs);
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
@@ -108,7 +100,6 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   const int64_t stride = (int64_t)gridDim.x * STREAM_THREADS;
   int64_t pair = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
   const bool base_odd = (index_base & 1ull) != 0;
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ DOM_SPAWN;
   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
 
   // first loads are issued before waiting for the table
@@ -137,23 +128,21 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     uint32_t wp0, wv0, wp1, wv1;
     {
       const uint64_t pidx = g0 >> 1;
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi),
-                                    k0, k1);
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
       if (!base_odd) {
         wp0 = r.x; wv0 = r.y; wp1 = r.z; wv1 = r.w;
       } else {
         const uint64_t pidx1 = pidx + 1;
-        const uint4 r1 = philox4x32_10(
-            make_uint4((uint32_t)pidx1, (uint32_t)(pidx1 >> 32), s_lo, s_hi), k0, k1);
+        const uint4 r1 = philox4x32_10(make_uint4((uint32_t)pidx1, (uint32_t)(pidx1 >> 32), s_lo, s_hi), keys);
         wp0 = r.z; wv0 = r.w; wp1 = r1.x; wv1 = r1.y;
       }
     }
 
-    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, ov0, ov1, f0, f1;
-    slide_board<true>(b.x, b.y, sact[a2 & 3u], slut, glut, n0l, n0h, rw0, ov0);
-    slide_board<true>(b.z, b.w, sact[(a2 >> 8) & 3u], slut, glut, n1l, n1h, rw1, ov1);
-    finish_board(b.x, b.y, n0l, n0h, ov0, wp0, wv0, p4, HAS_OVERRIDE ? (o2 & 0xFFu) : 0xFFu, f0);
-    finish_board(b.z, b.w, n1l, n1h, ov1, wp1, wv1, p4, HAS_OVERRIDE ? (o2 >> 8) : 0xFFu, f1);
+    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, f0, f1, c0, c1;
+    slide_board<true>(b.x, b.y, a2 & 3u, tabs, slut, glut, n0l, n0h, rw0, f0, c0);
+    slide_board<true>(b.z, b.w, (a2 >> 8) & 3u, tabs, slut, glut, n1l, n1h, rw1, f1, c1);
+    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, wp0, wv0, p4, o2 & 0xFFu, f0);
+    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, wp1, wv1, p4, o2 >> 8, f1);
 
     st_stream_v4(next2 + pair, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v2(reward2 + pair, make_uint2(rw0, rw1));
@@ -172,8 +161,8 @@ __global__ void __launch_bounds__(256)
                       uint8_t* __restrict__ flags, int64_t n, const uint32_t* __restrict__ glut,
                       uint64_t seed, uint64_t step, uint64_t index_base, uint32_t p4,
                       const uint8_t* __restrict__ override1) {
-  __shared__ ActXform sact[4];
-  if (threadIdx.x < 4) sact[threadIdx.x] = act_xform((int)threadIdx.x);
+  __shared__ SmemTabs tabs;
+  fill_tabs(&tabs);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -182,9 +171,9 @@ __global__ void __launch_bounds__(256)
   const uint64_t g = index_base + (uint64_t)i;
   const uint4 r = philox_at(seed, DOM_SPAWN, g >> 1, step);
   const uint32_t wp = (g & 1ull) ? r.z : r.x, wv = (g & 1ull) ? r.w : r.y;
-  uint32_t nl, nh, rw, ov, f;
-  slide_board<false>(lo, hi, sact[actions[i] & 3u], nullptr, glut, nl, nh, rw, ov);
-  finish_board(lo, hi, nl, nh, ov, wp, wv, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
+  uint32_t nl, nh, rw, f, ch;
+  slide_board<false>(lo, hi, actions[i] & 3u, &tabs, nullptr, glut, nl, nh, rw, f, ch);
+  finish_board<HAS_OVERRIDE>(nl, nh, ch, wp, wv, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
   next[i] = ((uint64_t)nh << 32) | nl;
   reward[i] = (int32_t)rw;
   flags[i] = (uint8_t)f;
@@ -192,28 +181,21 @@ __global__ void __launch_bounds__(256)
 
 // ---- all four actions per board (BASELINE.json config 2) ------------------------------------------
 template <bool SMEM, bool HAS_OVERRIDE>
-__device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const uint32_t* slut,
+__device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemTabs* tabs, const uint32_t* slut,
                                            const uint32_t* __restrict__ glut, uint32_t wp,
                                            uint32_t wv, uint32_t p4, uint32_t ovr4, uint32_t nl[4],
                                            uint32_t nh[4], uint32_t rw[4], uint32_t& flags) {
-  uint32_t legal = 0, ovf = 0, bad = 0;
+  uint32_t legal = 0, extra = 0;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    uint32_t ov;
-    slide_board<SMEM>(lo, hi, act_xform(a), slut, glut, nl[a], nh[a], rw[a], ov);
-    ovf |= ov;
-    const bool changed = (nl[a] != lo) | (nh[a] != hi);
-    legal |= changed ? (1u << a) : 0u;
-    const uint32_t ovr = HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu;
-    if (ovr == B2048_SPAWN_NONE) {
-      uint32_t sl = nl[a], sh = nh[a];
-      spawn_kth_empty(sl, sh, wp, (wv < p4) ? 2u : 1u);
-      if (changed) { nl[a] = sl; nh[a] = sh; }
-    } else if (changed) {
-      if (!spawn_at(nl[a], nh[a], ovr & 0xFu, (ovr >> 4) & 0xFu)) bad = B2048_FLAG_BADSPAWN;
-    }
+    uint32_t f, ch;
+    slide_board<SMEM>(lo, hi, (uint32_t)a, tabs, slut, glut, nl[a], nh[a], rw[a], f, ch);
+    legal |= ch ? (1u << a) : 0u;    // legal == the move changes the board
+    extra |= f & B2048_FLAG_OVERFLOW;
+    finish_board<HAS_OVERRIDE>(nl[a], nh[a], ch, wp, wv, p4, HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu, f);
+    extra |= f & B2048_FLAG_BADSPAWN;
   }
-  flags = legal | (legal ? 0u : B2048_FLAG_DONE) | (ovf ? B2048_FLAG_OVERFLOW : 0u) | bad;
+  flags = legal | (legal ? 0u : (uint32_t)B2048_FLAG_DONE) | extra;
 }
 
 template <bool HAS_OVERRIDE>
@@ -222,6 +204,9 @@ __global__ void __launch_bounds__(256)
                      uint4* __restrict__ reward4, uint8_t* __restrict__ flags, int64_t n,
                      const uint32_t* __restrict__ glut, uint64_t seed, uint64_t step,
                      uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
+  __shared__ SmemTabs tabs;
+  fill_tabs(&tabs);
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t bd = boards[i];
@@ -230,7 +215,7 @@ __global__ void __launch_bounds__(256)
   const uint4 r = philox_at(seed, DOM_SPAWN, g >> 1, step);
   const uint32_t wp = (g & 1ull) ? r.z : r.x, wv = (g & 1ull) ? r.w : r.y;
   uint32_t nl[4], nh[4], rw[4], f;
-  all4_board<false, HAS_OVERRIDE>(lo, hi, nullptr, glut, wp, wv, p4,
+  all4_board<false, HAS_OVERRIDE>(lo, hi, &tabs, nullptr, glut, wp, wv, p4,
                                   HAS_OVERRIDE ? override4[i] : 0xFFFFFFFFu, nl, nh, rw, f);
   st_stream_v4(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]));
   st_stream_v4(next4 + 2 * i + 1, make_uint4(nl[2], nh[2], nl[3], nh[3]));
@@ -349,7 +334,7 @@ cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint
     step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
         reinterpret_cast<const uint4*>(boards), reinterpret_cast<const uint16_t*>(actions),
         reinterpret_cast<uint4*>(next), reinterpret_cast<uint2*>(reward),
-        reinterpret_cast<uint16_t*>(flags), npairs, ctx->lut, seed, step, index_base, p4,
+        reinterpret_cast<uint16_t*>(flags), npairs, ctx->lut, philox_keys(seed, DOM_SPAWN), step, index_base, p4,
         reinterpret_cast<const uint16_t*>(ovr));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

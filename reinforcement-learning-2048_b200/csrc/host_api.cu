@@ -20,31 +20,41 @@ static std::vector<uint32_t> g_host_lut;
 // most once (leftmost pair first), compress.  Equals the reference's while-loop
 // (src/board.py:92-126) on every one of the 65536 rows (tests/test_oracle_golden.py proves it
 // against the reference's own outputs).  reward = sum of merged tile values (src/board.py:114).
-static uint32_t build_row_entry(uint32_t row) {
+static void move_row(const int in[4], int out[4], uint32_t* reward, bool* overflow) {
   int t[4], nt = 0;
-  for (int c = 0; c < 4; ++c) {
-    const int e = (row >> (4 * c)) & 0xF;
-    if (e) t[nt++] = e;
-  }
-  int out[4] = {0, 0, 0, 0}, no = 0;
-  uint32_t reward = 0;
-  bool overflow = false;
+  for (int c = 0; c < 4; ++c)
+    if (in[c]) t[nt++] = in[c];
+  int no = 0;
+  out[0] = out[1] = out[2] = out[3] = 0;
   for (int i = 0; i < nt; ++i) {
     if (i + 1 < nt && t[i] == t[i + 1]) {
       const int m = t[i] + 1;
-      reward += 1u << m;
-      if (m > 15) overflow = true;
+      *reward += 1u << m;
+      if (m > 15) *overflow = true;
       out[no++] = m & 0xF;
       ++i;
     } else {
       out[no++] = t[i];
     }
   }
+}
+
+static uint32_t build_row_entry(uint32_t row) {
+  int in[4], rev[4], out[4], tmp[4];
+  for (int c = 0; c < 4; ++c) {
+    in[c] = (row >> (4 * c)) & 0xF;
+    rev[3 - c] = in[c];
+  }
+  uint32_t reward = 0, r2 = 0;
+  bool overflow = false, o2 = false;
+  move_row(in, out, &reward, &overflow);
+  move_row(rev, tmp, &r2, &o2);                       // the same row moved RIGHT
+  const bool can_right = tmp[0] != rev[0] || tmp[1] != rev[1] || tmp[2] != rev[2] || tmp[3] != rev[3];
   uint32_t res = 0;
   for (int c = 0; c < 4; ++c) res |= (uint32_t)out[c] << (4 * c);
-  uint32_t r4 = reward >> 2;
-  if (r4 > 0x7FFFu) r4 = 0x7FFFu;  // only reachable together with overflow
-  return res | (r4 << 16) | (overflow ? 0x80000000u : 0u);
+  // 14-bit reward/4: exact for every non-overflow row except 0xEEEE (65536), see b2048_common.cuh
+  const uint32_t r4 = (reward >> 2) & 0x3FFFu;
+  return res | (r4 << 16) | (can_right ? 0x40000000u : 0u) | (overflow ? 0x80000000u : 0u);
 }
 
 static const std::vector<uint32_t>& host_lut() {

@@ -36,14 +36,23 @@ def test_row_table_equals_reference_rows(golden_dir):
     g = np.load(os.path.join(golden_dir, "rows.npz"))
     lut = env.row_lut_host()
     res = lut & 0xFFFF
-    rew4 = (lut >> 16) & 0x7FFF
+    rew4 = (lut >> 16) & 0x3FFF
+    can_right = (lut >> 30) & 1
     ovf = lut >> 31
     want_exp = np.where(g["result"] > 0, np.log2(np.maximum(g["result"], 1)).astype(np.int64), 0)
     is_ovf = (g["result"] > 32768).any(axis=1)
     want = (want_exp[:, 0] | (want_exp[:, 1] << 4) | (want_exp[:, 2] << 8) | (want_exp[:, 3] << 12))
     ok = ~is_ovf
     assert np.array_equal(res[ok], want[ok])
-    assert np.array_equal(rew4[ok] * 4, g["reward"][ok])
+    ok_r = ok.copy()
+    ok_r[0xEEEE] = False                     # reward 65536 does not fit 14 bits: added on the global path
+    assert np.array_equal(rew4[ok_r] * 4, g["reward"][ok_r])
+    assert g["reward"][0xEEEE] == 65536 and rew4[0xEEEE] == 0
+    # RIGHT bit: the reversed row changes under the reference's left move
+    rows = np.arange(65536)
+    rev = ((rows & 0xF) << 12) | ((rows & 0xF0) << 4) | ((rows & 0xF00) >> 4) | ((rows & 0xF000) >> 12)
+    tiles_rev = np.stack([np.where((rev >> (4 * c)) & 0xF, 1 << ((rev >> (4 * c)) & 0xF), 0) for c in range(4)], axis=1)
+    assert np.array_equal(can_right.astype(bool), (g["result"][rev] != tiles_rev).any(axis=1))
     assert np.array_equal(ovf.astype(bool), is_ovf)
     assert is_ovf.sum() > 0
 

@@ -1,0 +1,53 @@
+"""CPU: the kernel's SWAR pipeline (Python bit-model in tests/swar_model.py, fed with the row table
+the C-ABI library builds on the host) against the reference goldens — slide, reward, legal mask,
+done, changed, overflow for 3003 boards x 4 actions, plus the spawn selection vs the oracle."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from b2048 import env
+from oracle import board_oracle as bo
+import swar_model as sm
+
+
+def test_model_matches_reference_boards(golden_dir):
+    g = np.load(os.path.join(golden_dir, "boards.npz"))
+    lut = env.row_lut_host()
+    st = g["state"]
+    packed = bo.pack(st)
+    rng = np.random.default_rng(0)
+    n_spawn = 0
+    for i in range(0, len(st), 2):
+        b = int(packed[i])
+        lo, hi = b & sm.M32, b >> 32
+        for a in range(4):
+            nl, nh, rew, flags = sm.slide_board(lut, lo, hi, a)
+            assert flags & 0x0F == int(g["legal"][i]), (i, a)
+            assert bool(flags & 0x10) == (int(g["legal"][i]) == 0)
+            assert bool(flags & 0x20) == bool(g["legal"][i] >> a & 1)
+            sl = g["slide"][i, a]
+            if sl.max() > 32768:
+                assert flags & 0x40
+                continue
+            assert not flags & 0x40
+            want = int(bo.pack(sl[None])[0])
+            assert ((nh << 32) | nl) == want and rew == int(g["reward"][i, a]), (i, a)
+            if flags & 0x20 and i % 4 == 0:
+                w = int(rng.integers(0, 2 ** 32))
+                sl2, sh2, cnt = sm.spawn_kth_empty(nl, nh, w, 1)
+                ne = int((sl == 0).sum())
+                assert cnt == ne
+                t = sl.copy()
+                t[np.nonzero(sl == 0)[0][(w * ne) >> 32]] = 2
+                assert ((sh2 << 32) | sl2) == int(bo.pack(t[None])[0])
+                n_spawn += 1
+    assert n_spawn > 500
+
+
+def test_row_0xEEEE_reward_goes_through_the_global_path():
+    lut = env.row_lut_host()
+    # [16384]*4 in one row: two merges of 32768 = 65536, does not fit the 14-bit field
+    nl, nh, rew, flags = sm.slide_board(lut, 0xEEEE, 0, 2)
+    assert rew == 65536 and nl == 0x00FF and not flags & 0x40
