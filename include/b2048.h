@@ -56,7 +56,8 @@ extern "C" {
  * 2 => "4"); 0xFF = no override for this board (use the Philox stream). */
 #define B2048_SPAWN_NONE 0xFFu
 
-/* p4_threshold: a spawned tile is a "4" iff a fresh 32-bit Philox word is < p4_threshold.
+/* p4_threshold: a spawned tile is a "4" iff (w << 16) < p4_threshold (32-bit unsigned), i.e. the
+ * low 16 bits of the board's Philox word w are a uniform fraction compared with p4_threshold/2^32.
  * 0x1999999A = 10 % (north_star), 0x80000000 = 50 % (the reference, src/board.py:12,49). */
 #define B2048_P4_TEN_PERCENT   0x1999999Au
 #define B2048_P4_FIFTY_PERCENT 0x80000000u
@@ -84,8 +85,10 @@ int b2048_copy_row_lut_host(uint32_t* out65536);
  *   next[i]   = slide/merge of boards[i] by actions[i], plus one spawned tile iff changed
  *   reward[i] = sum of merged tile values of this move
  *   flags[i]  = B2048_FLAG_* (legal mask and done are properties of the INPUT board)
- * Spawn: cell = k-th empty cell (row-major) with k uniform from Philox4x32-10 keyed by `seed`,
- * counter (global board index = index_base + i, `step`); value "4" iff word < p4_threshold.
+ * Spawn: board g = index_base + i owns one 32-bit word w = word (g & 3) of the Philox4x32-10 call
+ * with key `seed` and counter (g >> 2, `step`); cell = k-th empty cell of the slid board
+ * (row-major) with k = floor(w * n_empty / 2^32); value "4" iff (w << 16) < p4_threshold.
+ * The result depends only on (seed, step, g, board, action), never on n or on the sharding.
  * spawn_override (nullable, n bytes) replays a given (cell, value) instead — the parity hook.
  * actions[i] > 3 is treated as actions[i] & 3. */
 int b2048_step(const uint64_t* boards, const uint8_t* actions, uint64_t* next, int32_t* reward,

@@ -186,18 +186,19 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 #define DOM_SPAWN 0x00000000u
 #define DOM_RESET 0x5BD1E995u
 
-static void spawn_words(uint64_t seed, uint64_t step, uint64_t g, uint32_t* w_pos, uint32_t* w_val) {
-  const uint64_t pidx = g >> 1;
+/* The library's spawn stream (include/b2048.h): board g uses word (g & 3) of the Philox4x32-10
+ * call with counter (g >> 2, step) and key (seed ^ domain). */
+static uint32_t spawn_word(uint64_t seed, uint64_t step, uint64_t g) {
+  const uint64_t pidx = g >> 2;
   const uint32_t ctr[4] = {(uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ DOM_SPAWN};
   uint32_t o[4];
   oracle_philox4x32_10(ctr, key, o);
-  *w_pos = (g & 1) ? o[2] : o[0];
-  *w_val = (g & 1) ? o[3] : o[1];
+  return o[g & 3];
 }
 
 /* Batched step on packed boards with the library's documented spawn rule (include/b2048.h):
- * cell = k-th empty (row-major), k = floor(w_pos * n_empty / 2^32); "4" iff w_val < p4_threshold;
+ * cell = k-th empty (row-major), k = floor(w * n_empty / 2^32); "4" iff (w << 16) < p4_threshold;
  * spawn_override[i] != 0xFF replays (cell | exp << 4). */
 static void step_packed_range(const uint64_t* boards, const uint8_t* actions, uint64_t* next,
                               int32_t* reward, uint8_t* flags, int64_t begin, int64_t end,
@@ -216,11 +217,10 @@ static void step_packed_range(const uint64_t* boards, const uint8_t* actions, ui
     } else {
       f = oracle_step_tiles(in, actions[i] & 3, -1, 0, out, &r);
       if (f & F_CHANGED) {
-        uint32_t wp, wv;
-        spawn_words(seed, step, index_base + (uint64_t)i, &wp, &wv);
+        const uint32_t w = spawn_word(seed, step, index_base + (uint64_t)i);
         const int ne = count_empty(out);
-        const int rank = (int)(((uint64_t)wp * (uint64_t)ne) >> 32);
-        oracle_populate(out, rank, (wv < p4_threshold) ? 4 : 2);
+        const int rank = (int)(((uint64_t)w * (uint64_t)ne) >> 32);
+        oracle_populate(out, rank, ((uint32_t)(w << 16) < p4_threshold) ? 4 : 2);
       }
     }
     /* 32768 + 32768 does not fit a nibble: the library flags it and leaves next/reward unspecified */

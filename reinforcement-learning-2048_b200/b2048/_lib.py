@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2048.so")
+LIB_PATH = os.environ.get("B2048_LIB") or os.path.join(_HERE, "libb2048.so")   # B2048_LIB: kernel-variant experiments only
 
 c_void_p, c_int, c_int64, c_uint64, c_uint32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                 ctypes.c_uint64, ctypes.c_uint32)

@@ -113,7 +113,16 @@ __host__ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t doma
 // operation has an equivalent on the FMA pipe it is written that way on purpose:
 //   x >> k  ->  __umulhi(x, 1 << (32-k))   (IMAD.HI)      x << k -> x * (1 << k)  (IMAD.SHL)
 //   a | b with disjoint bits -> a + b / a * m + b          (IMAD)
-__device__ __forceinline__ uint32_t shr_fma(uint32_t v, int k) { return __umulhi(v, 1u << (32 - k)); }
+#ifndef B2048_SHR_FMA
+#define B2048_SHR_FMA 0
+#endif
+__device__ __forceinline__ uint32_t shr_fma(uint32_t v, int k) {
+#if B2048_SHR_FMA
+  return __umulhi(v, 1u << (32 - k));   // IMAD.HI: 4 cycles on the FMA pipe
+#else
+  return v >> k;                        // SHF: 2 cycles on the ALU pipe
+#endif
+}
 
 // bit 3 of every nibble set iff the nibble is non-zero (carry-free: 7+7 < 16).
 __device__ __forceinline__ uint32_t nz3(uint32_t v) {
@@ -161,18 +170,23 @@ struct ActXform {
   uint32_t mul_l;    // 1 << s
   uint32_t mul_r;    // 1 << (32 - s)
   uint32_t mask;
-  uint32_t pad0, pad1, pad2;
+  uint32_t shift;    // s
+  uint32_t sel_fwd_hi, sel_inv_hi;
 };
 
 __host__ __device__ constexpr ActXform act_xform(int a) {
-  return a == 0   ? ActXform{0x6240u | (0x7351u << 16), 0x6240u | (0x7351u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 0, 0, 0}
-         : a == 1 ? ActXform{0x0426u | (0x1537u << 16), 0x5173u | (0x4062u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 0, 0, 0}
-         : a == 2 ? ActXform{0x3210u | (0x7654u << 16), 0x3210u | (0x7654u << 16), 1u << 4, 1u << 28, 0u, 0, 0, 0}
-                  : ActXform{0x2301u | (0x6745u << 16), 0x2301u | (0x6745u << 16), 1u << 4, 1u << 28, 0x0F0F0F0Fu, 0, 0, 0};
+  return a == 0   ? ActXform{0x6240u | (0x7351u << 16), 0x6240u | (0x7351u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 12u, 0x7351u, 0x7351u}
+         : a == 1 ? ActXform{0x0426u | (0x1537u << 16), 0x5173u | (0x4062u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 12u, 0x1537u, 0x4062u}
+         : a == 2 ? ActXform{0x3210u | (0x7654u << 16), 0x3210u | (0x7654u << 16), 1u << 4, 1u << 28, 0u, 4u, 0x7654u, 0x7654u}
+                  : ActXform{0x2301u | (0x6745u << 16), 0x2301u | (0x6745u << 16), 1u << 4, 1u << 28, 0x0F0F0F0Fu, 4u, 0x6745u, 0x6745u};
 }
 
 __device__ __forceinline__ uint32_t delta_swap(uint32_t v, const ActXform& x) {
+#if B2048_SHR_FMA
   const uint32_t t = (v ^ __umulhi(v, x.mul_r)) & x.mask;
+#else
+  const uint32_t t = (v ^ (v >> x.shift)) & x.mask;
+#endif
   return v ^ t ^ (t * x.mul_l);
 }
 
@@ -254,7 +268,7 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
                                             uint32_t& flags, uint32_t& changed) {
   const ActXform x = tabs->act[a];
   uint32_t zl = __byte_perm(lo, hi, x.sel_fwd);
-  uint32_t zh = __byte_perm(lo, hi, shr_fma(x.sel_fwd, 16));
+  uint32_t zh = __byte_perm(lo, hi, x.sel_fwd_hi);
   zl = delta_swap(zl, x);
   zh = delta_swap(zh, x);
   uint32_t e0, e1, e2, e3, extra;
@@ -285,7 +299,7 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
   wl = delta_swap(wl, x);
   wh = delta_swap(wh, x);
   olo = __byte_perm(wl, wh, x.sel_inv);
-  ohi = __byte_perm(wl, wh, shr_fma(x.sel_inv, 16));
+  ohi = __byte_perm(wl, wh, x.sel_inv_hi);
 }
 
 // ---- spawn ---------------------------------------------------------------------------------------

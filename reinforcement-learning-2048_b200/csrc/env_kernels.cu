@@ -7,8 +7,8 @@
 //
 // Streaming kernel (`step_stream_kernel`): persistent, one 1024-thread CTA per SM, the row table
 // staged once per CTA into 224 KB of shared memory with cp.async.bulk (TMA bulk copy, UBLKCP),
-// two boards per thread per iteration through one 128-bit load / store, one Philox4x32-10 call
-// per board pair.  Small batches use `step_small_kernel`, which reads the L2-resident table
+// four boards per thread per iteration through 128-bit loads / stores, one Philox4x32-10 call
+// per four boards.  Small batches use `step_small_kernel`, which reads the L2-resident table
 // directly and so skips the 224 KB staging.
 #include "b2048_common.cuh"
 
@@ -51,33 +51,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
-// Per-board tail shared by both step kernels: spawn one tile iff the move changed the board.
-//   w_pos / w_val : the board's two Philox words
-//   ovr           : spawn override byte (B2048_SPAWN_NONE = none)
+// Per-board tail shared by the step kernels: spawn one tile iff the move changed the board.
+//   w   : the board's Philox word (position from the high bits, value from the low 16 bits)
+//   ovr : spawn override byte (B2048_SPAWN_NONE = none)
 template <bool HAS_OVERRIDE>
-__device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w_pos,
-                                             uint32_t w_val, uint32_t p4, uint32_t ovr, uint32_t& flags) {
-  const uint32_t e = changed ? ((w_val < p4) ? 2u : 1u) : 0u;
+__device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
+  const uint32_t e = changed ? (((w << 16) < p4) ? 2u : 1u) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w_pos, e);
+    spawn_kth_empty(nlo, nhi, w, e);
   } else if (changed) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
 }
 
+// The Philox word of global board g: word (g & 3) of the call with counter (g >> 2, step).
+__device__ __forceinline__ uint32_t pick_word(const uint4& r, uint32_t j) {
+  return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
+}
+
 constexpr int STREAM_THREADS = 1024;
 constexpr int STREAM_SMEM_BYTES = LUT_SMEM_BYTES + (int)sizeof(SmemTabs) + 16;  // row table + small tables + mbarrier
 
-// ---- streaming kernel: two boards per thread, table in shared memory -----------------------------
-// Requires: boards/next 16-byte aligned, actions/flags 2-byte aligned, reward 8-byte aligned,
-// n even (host wrapper peels the odd board / misaligned case into step_small_kernel).
+// ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
+// Requires 16-byte aligned boards/next/reward, 4-byte aligned actions/flags/override and n % 4 == 0
+// (the host wrapper sends the remainder and unaligned batches to step_small_kernel).
 template <bool HAS_OVERRIDE>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
-    step_stream_kernel(const uint4* __restrict__ boards2, const uint16_t* __restrict__ actions2,
-                       uint4* __restrict__ next2, uint2* __restrict__ reward2,
-                       uint16_t* __restrict__ flags2, int64_t npairs,
+    step_stream_kernel(const uint4* __restrict__ boards2, const uint32_t* __restrict__ actions4,
+                       uint4* __restrict__ next2, uint4* __restrict__ reward4,
+                       uint32_t* __restrict__ flags4, int64_t nquads,
                        const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
-                       uint64_t index_base, uint32_t p4, const uint16_t* __restrict__ override2) {
+                       uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
   SmemTabs* tabs = reinterpret_cast<SmemTabs*>(smem_raw + LUT_SMEM_BYTES);
@@ -98,58 +103,66 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   }
 
   const int64_t stride = (int64_t)gridDim.x * STREAM_THREADS;
-  int64_t pair = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
-  const bool base_odd = (index_base & 1ull) != 0;
+  int64_t quad = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+  const uint32_t base_mis = (uint32_t)index_base & 3u;
   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
 
   // first loads are issued before waiting for the table
-  uint4 b = make_uint4(0, 0, 0, 0);
-  uint32_t a2 = 0, o2 = 0xFFFFu;
-  if (pair < npairs) {
-    b = ld_stream_v4(boards2 + pair);
-    a2 = actions2[pair];
-    if (HAS_OVERRIDE) o2 = override2[pair];
+  uint4 ba = make_uint4(0, 0, 0, 0), bb = ba;
+  uint32_t a4 = 0, o4 = 0xFFFFFFFFu;
+  if (quad < nquads) {
+    ba = ld_stream_v4(boards2 + 2 * quad);
+    bb = ld_stream_v4(boards2 + 2 * quad + 1);
+    a4 = ld_stream_u32(actions4 + quad);
+    if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
   mbar_wait(bar, 0);
 
-  while (pair < npairs) {
-    // prefetch the next pair of this thread
-    const int64_t nxt = pair + stride;
-    uint4 bn = make_uint4(0, 0, 0, 0);
-    uint32_t an = 0, on = 0xFFFFu;
-    if (nxt < npairs) {
-      bn = ld_stream_v4(boards2 + nxt);
-      an = actions2[nxt];
-      if (HAS_OVERRIDE) on = override2[nxt];
+  while (quad < nquads) {
+    // prefetch this thread's next quad
+    const int64_t nxt = quad + stride;
+    uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+    uint32_t an = 0, on = 0xFFFFFFFFu;
+    if (nxt < nquads) {
+      na = ld_stream_v4(boards2 + 2 * nxt);
+      nb = ld_stream_v4(boards2 + 2 * nxt + 1);
+      an = ld_stream_u32(actions4 + nxt);
+      if (HAS_OVERRIDE) on = ld_stream_u32(override4 + nxt);
     }
 
-    // Philox: one call per aligned global pair; words (x,y) -> even board, (z,w) -> odd board
-    const uint64_t g0 = index_base + 2ull * (uint64_t)pair;
-    uint32_t wp0, wv0, wp1, wv1;
-    {
-      const uint64_t pidx = g0 >> 1;
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
-      if (!base_odd) {
-        wp0 = r.x; wv0 = r.y; wp1 = r.z; wv1 = r.w;
-      } else {
-        const uint64_t pidx1 = pidx + 1;
-        const uint4 r1 = philox4x32_10(make_uint4((uint32_t)pidx1, (uint32_t)(pidx1 >> 32), s_lo, s_hi), keys);
-        wp0 = r.z; wv0 = r.w; wp1 = r1.x; wv1 = r1.y;
+    // one Philox4x32-10 call per aligned group of four global board indices
+    const uint64_t g0 = index_base + 4ull * (uint64_t)quad;
+    const uint64_t pidx = g0 >> 2;
+    uint4 w = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
+    if (base_mis != 0) {  // uniform: index_base not a multiple of 4 -> the quad straddles two calls
+      const uint64_t p1 = pidx + 1;
+      const uint4 w1 = philox4x32_10(make_uint4((uint32_t)p1, (uint32_t)(p1 >> 32), s_lo, s_hi), keys);
+      uint32_t t[4];
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t q = base_mis + j;
+        t[j] = q < 4 ? pick_word(w, q) : pick_word(w1, q - 4);
       }
+      w = make_uint4(t[0], t[1], t[2], t[3]);
     }
 
     uint32_t n0l, n0h, n1l, n1h, rw0, rw1, f0, f1, c0, c1;
-    slide_board<true>(b.x, b.y, a2 & 3u, tabs, slut, glut, n0l, n0h, rw0, f0, c0);
-    slide_board<true>(b.z, b.w, (a2 >> 8) & 3u, tabs, slut, glut, n1l, n1h, rw1, f1, c1);
-    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, wp0, wv0, p4, o2 & 0xFFu, f0);
-    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, wp1, wv1, p4, o2 >> 8, f1);
+    slide_board<true>(ba.x, ba.y, a4 & 3u, tabs, slut, glut, n0l, n0h, rw0, f0, c0);
+    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.x, p4, o4 & 0xFFu, f0);
+    slide_board<true>(ba.z, ba.w, (a4 >> 8) & 3u, tabs, slut, glut, n1l, n1h, rw1, f1, c1);
+    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.y, p4, (o4 >> 8) & 0xFFu, f1);
+    st_stream_v4(next2 + 2 * quad, make_uint4(n0l, n0h, n1l, n1h));
+    uint32_t rw2, rw3, f2, f3;
+    slide_board<true>(bb.x, bb.y, (a4 >> 16) & 3u, tabs, slut, glut, n0l, n0h, rw2, f2, c0);
+    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.z, p4, (o4 >> 16) & 0xFFu, f2);
+    slide_board<true>(bb.z, bb.w, (a4 >> 24) & 3u, tabs, slut, glut, n1l, n1h, rw3, f3, c1);
+    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.w, p4, o4 >> 24, f3);
+    st_stream_v4(next2 + 2 * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
+    st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
+    flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
 
-    st_stream_v4(next2 + pair, make_uint4(n0l, n0h, n1l, n1h));
-    st_stream_v2(reward2 + pair, make_uint2(rw0, rw1));
-    flags2[pair] = (uint16_t)(f0 | (f1 << 8));
-
-    b = bn; a2 = an; o2 = on;
-    pair = nxt;
+    ba = na; bb = nb; a4 = an; o4 = on;
+    quad = nxt;
   }
 }
 
@@ -169,11 +182,10 @@ __global__ void __launch_bounds__(256)
   const uint64_t bd = boards[i];
   const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
   const uint64_t g = index_base + (uint64_t)i;
-  const uint4 r = philox_at(seed, DOM_SPAWN, g >> 1, step);
-  const uint32_t wp = (g & 1ull) ? r.z : r.x, wv = (g & 1ull) ? r.w : r.y;
+  const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
   uint32_t nl, nh, rw, f, ch;
   slide_board<false>(lo, hi, actions[i] & 3u, &tabs, nullptr, glut, nl, nh, rw, f, ch);
-  finish_board<HAS_OVERRIDE>(nl, nh, ch, wp, wv, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
+  finish_board<HAS_OVERRIDE>(nl, nh, ch, w, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
   next[i] = ((uint64_t)nh << 32) | nl;
   reward[i] = (int32_t)rw;
   flags[i] = (uint8_t)f;
@@ -182,8 +194,8 @@ __global__ void __launch_bounds__(256)
 // ---- all four actions per board (BASELINE.json config 2) ------------------------------------------
 template <bool SMEM, bool HAS_OVERRIDE>
 __device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemTabs* tabs, const uint32_t* slut,
-                                           const uint32_t* __restrict__ glut, uint32_t wp,
-                                           uint32_t wv, uint32_t p4, uint32_t ovr4, uint32_t nl[4],
+                                           const uint32_t* __restrict__ glut, uint32_t w,
+                                           uint32_t p4, uint32_t ovr4, uint32_t nl[4],
                                            uint32_t nh[4], uint32_t rw[4], uint32_t& flags) {
   uint32_t legal = 0, extra = 0;
 #pragma unroll
@@ -192,7 +204,7 @@ __device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemT
     slide_board<SMEM>(lo, hi, (uint32_t)a, tabs, slut, glut, nl[a], nh[a], rw[a], f, ch);
     legal |= ch ? (1u << a) : 0u;    // legal == the move changes the board
     extra |= f & B2048_FLAG_OVERFLOW;
-    finish_board<HAS_OVERRIDE>(nl[a], nh[a], ch, wp, wv, p4, HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu, f);
+    finish_board<HAS_OVERRIDE>(nl[a], nh[a], ch, w, p4, HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu, f);
     extra |= f & B2048_FLAG_BADSPAWN;
   }
   flags = legal | (legal ? 0u : (uint32_t)B2048_FLAG_DONE) | extra;
@@ -212,10 +224,9 @@ __global__ void __launch_bounds__(256)
   const uint64_t bd = boards[i];
   const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
   const uint64_t g = index_base + (uint64_t)i;
-  const uint4 r = philox_at(seed, DOM_SPAWN, g >> 1, step);
-  const uint32_t wp = (g & 1ull) ? r.z : r.x, wv = (g & 1ull) ? r.w : r.y;
+  const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
   uint32_t nl[4], nh[4], rw[4], f;
-  all4_board<false, HAS_OVERRIDE>(lo, hi, &tabs, nullptr, glut, wp, wv, p4,
+  all4_board<false, HAS_OVERRIDE>(lo, hi, &tabs, nullptr, glut, w, p4,
                                   HAS_OVERRIDE ? override4[i] : 0xFFFFFFFFu, nl, nh, rw, f);
   st_stream_v4(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]));
   st_stream_v4(next4 + 2 * i + 1, make_uint4(nl[2], nh[2], nl[3], nh[3]));
@@ -324,21 +335,21 @@ cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint
                         uint64_t* next, int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed,
                         uint64_t step, uint64_t index_base, uint32_t p4, const uint8_t* ovr,
                         cudaStream_t st) {
-  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next)) & 15u) == 0 &&
-                       (reinterpret_cast<uintptr_t>(reward) & 7u) == 0 &&
+  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next) |
+                         reinterpret_cast<uintptr_t>(reward)) & 15u) == 0 &&
                        ((reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(flags) |
-                         reinterpret_cast<uintptr_t>(ovr)) & 1u) == 0;
+                         reinterpret_cast<uintptr_t>(ovr)) & 3u) == 0;
   int64_t done = 0;
   if (aligned && n >= STREAM_MIN_BOARDS) {
-    const int64_t npairs = n / 2;
+    const int64_t nquads = n / 4;
     step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
-        reinterpret_cast<const uint4*>(boards), reinterpret_cast<const uint16_t*>(actions),
-        reinterpret_cast<uint4*>(next), reinterpret_cast<uint2*>(reward),
-        reinterpret_cast<uint16_t*>(flags), npairs, ctx->lut, philox_keys(seed, DOM_SPAWN), step, index_base, p4,
-        reinterpret_cast<const uint16_t*>(ovr));
+        reinterpret_cast<const uint4*>(boards), reinterpret_cast<const uint32_t*>(actions),
+        reinterpret_cast<uint4*>(next), reinterpret_cast<uint4*>(reward),
+        reinterpret_cast<uint32_t*>(flags), nquads, ctx->lut, philox_keys(seed, DOM_SPAWN), step,
+        index_base, p4, reinterpret_cast<const uint32_t*>(ovr));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    done = npairs * 2;
+    done = nquads * 4;
   }
   if (done < n) {
     const int64_t m = n - done;
