@@ -124,13 +124,34 @@ __device__ __forceinline__ uint32_t shr_fma(uint32_t v, int k) {
 #endif
 }
 
-// bit 3 of every nibble set iff the nibble is non-zero (carry-free: 7+7 < 16).
-__device__ __forceinline__ uint32_t nz3(uint32_t v) {
-  return (((v & 0x77777777u) + 0x77777777u) | v) & 0x88888888u;
+// t + 0x77777777 (the carry-free nibble add of the non-zero tests).  `one` is a runtime 1 (read from
+// shared memory, so ptxas cannot fold it): t * one + c is issued as IMAD on the FMA pipe instead of
+// an integer add on the ALU pipe.  Measured on B200: no gain (0.4335 vs 0.4294 ms per 64Mi boards;
+// ptxas already balances plain adds across both pipes), so the default is the plain add.
+#ifndef B2048_ADD_FMA
+#define B2048_ADD_FMA 0
+#endif
+__device__ __forceinline__ uint32_t add7(uint32_t t, uint32_t one) {
+#if B2048_ADD_FMA
+  return t * one + 0x77777777u;
+#else
+  (void)one;
+  return t + 0x77777777u;
+#endif
 }
-// same for a ^ b, WITHOUT the final mask (bits other than bit 3 of each nibble are garbage)
-__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b) {
-  return (((a ^ b) & 0x77777777u) + 0x77777777u) | (a ^ b);
+
+// bit 3 of every nibble set iff the nibble is non-zero (carry-free: 7+7 < 16).
+__device__ __forceinline__ uint32_t nz3(uint32_t v, uint32_t one = 1u) {
+  return (add7(v & 0x77777777u, one) | v) & 0x88888888u;
+}
+// same for a ^ b, WITHOUT the final mask (bits other than bit 3 of each nibble are garbage).
+// Two 3-input LOP3s, written as lop3 so that ptxas does not split the xor out (one ALU op more).
+__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b, uint32_t one = 1u) {
+  uint32_t t, r;
+  asm("lop3.b32 %0, %1, %2, 0x77777777, 0x28;" : "=r"(t) : "r"(a), "r"(b));   // (a ^ b) & 0x7777...
+  t = add7(t, one);
+  asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(r) : "r"(t), "r"(a), "r"(b));   // t | (a ^ b)
+  return r;
 }
 
 // Legal-move mask (bits: up, down, left, right) of a board, without the row table: a move toward
@@ -207,10 +228,13 @@ __host__ __device__ constexpr uint32_t zframe_to_legal(int a, uint32_t m) {
 struct SmemTabs {
   ActXform act[4];        // 128 B
   uint8_t legal[4][16];   //  64 B
+  uint32_t one;           // runtime 1 for add7()
+  uint32_t pad[3];
 };
 
 __device__ __forceinline__ void fill_tabs(SmemTabs* t) {
   if (threadIdx.x < 4) t->act[threadIdx.x] = act_xform((int)threadIdx.x);
+  if (threadIdx.x == 0) t->one = 1u;
   if (threadIdx.x < 64) t->legal[threadIdx.x >> 4][threadIdx.x & 15] =
       (uint8_t)zframe_to_legal((int)(threadIdx.x >> 4), threadIdx.x & 15u);
 }
@@ -228,15 +252,24 @@ constexpr uint32_t ENTRY_RIGHT = 0x40000000u, ENTRY_OVF = 0x80000000u;
 __device__ __forceinline__ uint32_t lut_at(const uint32_t* base, uint32_t byte_off) {
   return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(base) + byte_off);
 }
-static __device__ __noinline__ void lookup4_global(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut,
-                                            uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3,
-                                            uint32_t& extra) {
+__device__ __forceinline__ void lookup4_global(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut,
+                                               uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3,
+                                               uint32_t& extra) {
   const uint32_t i0 = zl & 0xFFFFu, i1 = zl >> 16, i2 = zh & 0xFFFFu, i3 = zh >> 16;
   e0 = __ldg(glut + i0);
   e1 = __ldg(glut + i1);
   e2 = __ldg(glut + i2);
   e3 = __ldg(glut + i3);
   extra = ((i0 == 0xEEEEu) + (i1 == 0xEEEEu) + (i2 == 0xEEEEu) + (i3 == 0xEEEEu)) * 65536u;
+}
+// out-of-line copy for the rare miss of the shared-memory table (keeps the hot loop small)
+static __device__ __noinline__ uint4 lookup4_global_cold(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut,
+                                                         uint32_t* extra) {
+  uint4 e;
+  uint32_t x;
+  lookup4_global(zl, zh, glut, e.x, e.y, e.z, e.w, x);
+  *extra = x;
+  return e;
 }
 template <bool SMEM>
 __device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t* slut,
@@ -245,12 +278,13 @@ __device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t
   if (SMEM) {
     const uint32_t mx = __vmaxu2(zl, zh);
     if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
-      lookup4_global(zl, zh, glut, e0, e1, e2, e3, extra);
+      const uint4 e = lookup4_global_cold(zl, zh, glut, &extra);
+      e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
     } else {
       e0 = lut_at(slut, (zl * 4u) & 0x3FFFCu);
-      e1 = lut_at(slut, shr_fma(zl, 14) & 0x3FFFCu);
+      e1 = lut_at(slut, __byte_perm(zl, 0u, 0x4432) * 4u);   // PRMT + shift-add: one ALU op less than SHF + LOP3
       e2 = lut_at(slut, (zh * 4u) & 0x3FFFCu);
-      e3 = lut_at(slut, shr_fma(zh, 14) & 0x3FFFCu);
+      e3 = lut_at(slut, __byte_perm(zh, 0u, 0x4432) * 4u);
       extra = 0;
     }
   } else {
@@ -261,11 +295,11 @@ __device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t
 // Slide + merge one board by one action, and derive the legal mask of the INPUT board in the
 // transformed frame.  Outputs: slid board (no spawn), reward, flags (legal | done | changed |
 // overflow).
-template <bool SMEM>
+template <bool SMEM, bool LEGAL = true>
 __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a, const SmemTabs* tabs,
                                             const uint32_t* slut, const uint32_t* __restrict__ glut,
                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward,
-                                            uint32_t& flags, uint32_t& changed) {
+                                            uint32_t& flags, uint32_t& changed, uint32_t one = 1u) {
   const ActXform x = tabs->act[a];
   uint32_t zl = __byte_perm(lo, hi, x.sel_fwd);
   uint32_t zh = __byte_perm(lo, hi, x.sel_fwd_hi);
@@ -285,16 +319,20 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
   // transformed-frame legality: left = changed, right = any row's RIGHT bit, and the
   // perpendicular axis by SWAR on z: pair (row r, row r+1) sits at row r.
   changed = (wl ^ zl) | (wh ^ zh);
-  const uint32_t n_l = nz3(zl), n_h = nz3(zh);
-  const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = shr_fma(zh, 16);
-  const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
-  const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = shr_fma(n_h, 16);
-  const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
-  const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
-  const uint32_t m = (changed ? 1u : 0u) | ((fl & 0x40004000u) ? 2u : 0u) | (up ? 4u : 0u) |
-                     ((dn_l | (dn_h & 0x0000FFFFu)) ? 8u : 0u);
-  flags = tabs->legal[a][m] | (changed ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
-          ((fl & 0x80008000u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u);
+  if (LEGAL) {
+    const uint32_t n_l = nz3(zl, one), n_h = nz3(zh, one);
+    const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = shr_fma(zh, 16);
+    const uint32_t ne_l = ne3_dirty(zl, v_l, one), ne_h = ne3_dirty(zh, v_h, one);
+    const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = shr_fma(n_h, 16);
+    const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
+    const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
+    const uint32_t m = (changed ? 1u : 0u) | ((fl & 0x40004000u) ? 2u : 0u) | (up ? 4u : 0u) |
+                       ((dn_l | (dn_h & 0x0000FFFFu)) ? 8u : 0u);
+    flags = tabs->legal[a][m] | (changed ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
+            ((fl & 0x80008000u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u);
+  } else {
+    flags = (fl & 0x80008000u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u;
+  }
 
   wl = delta_swap(wl, x);
   wh = delta_swap(wh, x);
@@ -303,12 +341,12 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
 }
 
 // ---- spawn ---------------------------------------------------------------------------------------
-// Put exponent `e` (0 = nothing) into the k-th empty cell (row-major) where
-// k = floor(w_pos * n_empty / 2^32).  Requires at most 15 empty cells.
+// Put exponent e (0 = nothing) into the k-th empty cell (row-major) where
+// k = floor(w_pos * n_empty / 2^32).  Requires at most 15 empty cells.  `e29` = e << 29.
 __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint32_t w_pos,
-                                                uint32_t e) {
-  const uint32_t e3_lo = ~(((lo & 0x77777777u) + 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
-  const uint32_t e3_hi = ~(((hi & 0x77777777u) + 0x77777777u) | hi) & 0x88888888u;
+                                                uint32_t e29, uint32_t one = 1u) {
+  const uint32_t e3_lo = ~(add7(lo & 0x77777777u, one) | lo) & 0x88888888u;  // bit 3 of empty nibbles
+  const uint32_t e3_hi = ~(add7(hi & 0x77777777u, one) | hi) & 0x88888888u;
   const uint32_t e_lo = shr_fma(e3_lo, 3), e_hi = shr_fma(e3_hi, 3);
   // inclusive prefix counts per nibble: multiply by 0x11111111 (counts <= 15 never carry)
   const uint32_t p_lo = e_lo * 0x11111111u;
@@ -317,11 +355,12 @@ __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint
   const uint32_t cnt = shr_fma(p_hi, 28);
   const uint32_t tgt = __umulhi(w_pos, cnt) * 0x11111111u + 0x11111111u;  // (k+1) in every nibble
   // the chosen nibble is the empty one whose prefix count equals k+1
-  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt) & e3_lo;
-  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt) & e3_hi;
+  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt, one) & e3_lo;
+  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt, one) & e3_hi;
   // exactly one bit (bit 3 of the chosen nibble) is set across h_lo/h_hi; the cell is empty so + == |
-  lo += shr_fma(h_lo, 3) * e;
-  hi += shr_fma(h_hi, 3) * e;
+  // hi32(h * (e << 29)) = (h >> 3) * e: shift, scale and insert in one IMAD.HI each
+  lo = __umulhi(h_lo, e29) + lo;
+  hi = __umulhi(h_hi, e29) + hi;
 }
 
 // Insert exponent e at cell (0..15); returns false if the cell is occupied.

@@ -56,10 +56,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
 template <bool HAS_OVERRIDE>
 __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
-                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
-  const uint32_t e = changed ? (((w << 16) < p4) ? 2u : 1u) : 0u;
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags, uint32_t one = 1u) {
+  const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w, e);
+    spawn_kth_empty(nlo, nhi, w, e29, one);
   } else if (changed) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
   mbar_wait(bar, 0);
+  const uint32_t one = tabs->one;
 
   while (quad < nquads) {
     // prefetch this thread's next quad
@@ -147,16 +148,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     }
 
     uint32_t n0l, n0h, n1l, n1h, rw0, rw1, f0, f1, c0, c1;
-    slide_board<true>(ba.x, ba.y, a4 & 3u, tabs, slut, glut, n0l, n0h, rw0, f0, c0);
-    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.x, p4, o4 & 0xFFu, f0);
-    slide_board<true>(ba.z, ba.w, (a4 >> 8) & 3u, tabs, slut, glut, n1l, n1h, rw1, f1, c1);
-    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.y, p4, (o4 >> 8) & 0xFFu, f1);
+    slide_board<true>(ba.x, ba.y, a4 & 3u, tabs, slut, glut, n0l, n0h, rw0, f0, c0, one);
+    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.x, p4, o4 & 0xFFu, f0, one);
+    slide_board<true>(ba.z, ba.w, (a4 >> 8) & 3u, tabs, slut, glut, n1l, n1h, rw1, f1, c1, one);
+    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.y, p4, (o4 >> 8) & 0xFFu, f1, one);
     st_stream_v4(next2 + 2 * quad, make_uint4(n0l, n0h, n1l, n1h));
     uint32_t rw2, rw3, f2, f3;
-    slide_board<true>(bb.x, bb.y, (a4 >> 16) & 3u, tabs, slut, glut, n0l, n0h, rw2, f2, c0);
-    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.z, p4, (o4 >> 16) & 0xFFu, f2);
-    slide_board<true>(bb.z, bb.w, (a4 >> 24) & 3u, tabs, slut, glut, n1l, n1h, rw3, f3, c1);
-    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.w, p4, o4 >> 24, f3);
+    slide_board<true>(bb.x, bb.y, (a4 >> 16) & 3u, tabs, slut, glut, n0l, n0h, rw2, f2, c0, one);
+    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.z, p4, (o4 >> 16) & 0xFFu, f2, one);
+    slide_board<true>(bb.z, bb.w, (a4 >> 24) & 3u, tabs, slut, glut, n1l, n1h, rw3, f3, c1, one);
+    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.w, p4, o4 >> 24, f3, one);
     st_stream_v4(next2 + 2 * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
     flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
@@ -201,7 +202,7 @@ __device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemT
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     uint32_t f, ch;
-    slide_board<SMEM>(lo, hi, (uint32_t)a, tabs, slut, glut, nl[a], nh[a], rw[a], f, ch);
+    slide_board<SMEM, false>(lo, hi, (uint32_t)a, tabs, slut, glut, nl[a], nh[a], rw[a], f, ch);
     legal |= ch ? (1u << a) : 0u;    // legal == the move changes the board
     extra |= f & B2048_FLAG_OVERFLOW;
     finish_board<HAS_OVERRIDE>(nl[a], nh[a], ch, w, p4, HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu, f);
@@ -256,7 +257,7 @@ __global__ void reset_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t 
   const uint32_t e1 = (r.y < p4) ? 2u : 1u;
   uint32_t lo = 0, hi = 0;
   spawn_at(lo, hi, c1, e1);
-  spawn_kth_empty(lo, hi, r.z, (r.w < p4) ? 2u : 1u);
+  spawn_kth_empty(lo, hi, r.z, (r.w < p4) ? (2u << 29) : (1u << 29));
   boards[i] = ((uint64_t)hi << 32) | lo;
 }
 
