@@ -53,8 +53,10 @@ extern "C" {
 #define B2048_FLAG_BADSPAWN 0x80u /* spawn_override named a non-empty cell (nothing spawned)  */
 
 /* spawn_override byte: low nibble = cell index 4*r+c, high nibble = exponent (1 => "2",
- * 2 => "4"); 0xFF = no override for this board (use the Philox stream). */
+ * 2 => "4"); 0xFF = no override for this board (use the Philox stream); 0xFE = spawn nothing
+ * (slide-only result, e.g. Board2048._apply_action_to_vector). */
 #define B2048_SPAWN_NONE 0xFFu
+#define B2048_SPAWN_SKIP 0xFEu
 
 /* p4_threshold: a spawned tile is a "4" iff (w << 16) < p4_threshold (32-bit unsigned), i.e. the
  * low 16 bits of the board's Philox word w are a uniform fraction compared with p4_threshold/2^32.
@@ -112,6 +114,12 @@ int b2048_legal_mask(const uint64_t* boards, uint8_t* flags, int64_t n, void* st
 int b2048_reset(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
                 uint32_t p4_threshold, const uint8_t* where_flags, void* stream);
 
+/* One new tile on every board that has an empty cell (= Board2048._populate_empty_cell,
+ * src/board.py:41-51), in place, with the same Philox word assignment as b2048_step.  If
+ * `where_flags` is non-NULL only boards with (where_flags[i] & B2048_FLAG_CHANGED) get a tile. */
+int b2048_spawn(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
+                uint32_t p4_threshold, const uint8_t* where_flags, void* stream);
+
 /* int64 tiles [n,16] (reference `state`, row-major) <-> packed boards.  bad[i] (nullable) is set
  * to 1 if a tile is not 0 or a power of two in 2..32768. */
 int b2048_pack(const int64_t* tiles, uint64_t* boards, uint8_t* bad, int64_t n, void* stream);
@@ -139,14 +147,15 @@ int b2048_step_host(const uint64_t* h_boards, const uint8_t* h_actions, uint64_t
 
 /* Struct-of-arrays ring of `capacity` transitions (= the deque(maxlen) of 5-tuples,
  * src/dqn_lib.py:106,172).  All arrays are caller-allocated device memory; `head_size` is a
- * device int64[2] {head, size} that must be zero-initialised by the caller. */
+ * device int64[4] {head, size, auto sample counter, reserved}, zero-initialised by the caller. */
 typedef struct b2048_ring {
   uint64_t* s;        /* [capacity] packed state                 */
   uint64_t* s2;       /* [capacity] packed next state            */
   int32_t*  r;        /* [capacity] reward                       */
   uint8_t*  a;        /* [capacity] action                       */
   uint8_t*  d;        /* [capacity] done (0/1)                   */
-  int64_t*  head_size;/* device int64[2]: next write slot, number of valid entries */
+  int64_t*  head_size;/* device int64[4]: next write slot, number of valid entries,            */
+                      /*   automatic sample counter (see replay_sample), reserved              */
   int64_t   capacity;
 } b2048_ring;
 
@@ -160,7 +169,12 @@ int replay_append(const b2048_ring* ring, const uint64_t* s, const uint8_t* a, c
  * (= sample_experiences + extract_samples_conv/dense, src/dqn_lib.py:33-84).
  * Logical index 0 = oldest entry, like deque indexing.  idx_override (nullable, int64[B]) replays
  * the reference's np.random.randint draw; idx_out (nullable) receives the indices used.
- * states/next_states: f64 [B,16]; actions/rewards/dones: int64 [B]. */
+ * states/next_states: f64 [B,16]; actions/rewards/dones: int64 [B].
+ * Sample j uses word (j & 3) of the Philox4x32-10 call with key `seed` and counter (j >> 2, ctr):
+ * index = floor(word * size / 2^32).  ctr == B2048_CTR_AUTO takes the counter from the ring's
+ * device-side auto counter and increments it afterwards, so a captured CUDA graph draws a fresh
+ * batch on every replay. */
+#define B2048_CTR_AUTO 0xFFFFFFFFFFFFFFFFull
 int replay_sample(const b2048_ring* ring, int64_t B, uint64_t seed, uint64_t ctr,
                   const int64_t* idx_override, double* states, double* next_states,
                   int64_t* actions, int64_t* rewards, int64_t* dones, int64_t* idx_out,

@@ -17,6 +17,7 @@ P4_FIFTY_PERCENT = 0x80000000    # the reference: np.random.choice([2, 4]) (src/
 FLAG_LEGAL = 0x0F
 FLAG_DONE, FLAG_CHANGED, FLAG_OVERFLOW, FLAG_BADSPAWN = 0x10, 0x20, 0x40, 0x80
 SPAWN_NONE = 0xFF
+SPAWN_SKIP = 0xFE
 
 _U64 = (1 << 64) - 1
 
@@ -120,6 +121,21 @@ def reset(boards, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT, where_f
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b2048_reset(_ptr(boards), n, seed & _U64, step_index & _U64, index_base & _U64, p4,
                                           _ptr(where_flags), _stream(boards)), "b2048_reset")
+    return boards
+
+
+def spawn(boards, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT, where_flags=None):
+    """In place: one new tile per board with an empty cell (= Board2048._populate_empty_cell,
+    src/board.py:41-51); with `where_flags` only where the CHANGED bit is set."""
+    n = boards.numel()
+    dev = _dev(boards)
+    _lib.init(dev)
+    _chk(boards, torch.int64, name="boards")
+    if where_flags is not None:
+        _chk(where_flags, torch.uint8, n, "where_flags")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_spawn(_ptr(boards), n, seed & _U64, step_index & _U64, index_base & _U64, p4,
+                                          _ptr(where_flags), _stream(boards)), "b2048_spawn")
     return boards
 
 

@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import ctypes
 
+import numpy as np
+
 import torch
 
 from . import _lib
@@ -29,7 +31,7 @@ class ReplayRing:
         self.r = torch.zeros(self.capacity, dtype=torch.int32, **kw)
         self.a = torch.zeros(self.capacity, dtype=torch.uint8, **kw)
         self.d = torch.zeros(self.capacity, dtype=torch.uint8, **kw)
-        self.head_size = torch.zeros(2, dtype=torch.int64, **kw)
+        self.head_size = torch.zeros(4, dtype=torch.int64, **kw)   # head, size, auto sample counter, reserved
         self._ring = _lib.Ring(self.s.data_ptr(), self.s2.data_ptr(), self.r.data_ptr(), self.a.data_ptr(),
                                self.d.data_ptr(), self.head_size.data_ptr(), self.capacity)
 
@@ -44,6 +46,8 @@ class ReplayRing:
         with torch.cuda.device(self._dev):
             _lib.check(_lib.lib().replay_append(ctypes.byref(self._ring), _ptr(s), _ptr(a), _ptr(r), _ptr(s2),
                                                 _ptr(done_flags), n, _stream(s)), "replay_append")
+
+    CTR_AUTO = (1 << 64) - 1   # use (and bump) the ring's device-side counter: CUDA-graph friendly
 
     def sample(self, batch_size: int, seed=2051, ctr=0, idx_override=None, out=None, return_idx=False):
         """Fused sample + gather + unpack (src/dqn_lib.py:33-84).
@@ -70,3 +74,67 @@ class ReplayRing:
 
     def clear(self) -> None:
         self.head_size.zero_()
+
+
+class ReplayDeque:
+    """`collections.deque(maxlen=...)` look-alike for `dqn_lib` whose contents live in a GPU ring.
+
+    ``append((board, action, reward, next_board, done))`` takes the reference's 5-tuples
+    (src/dqn_lib.py:106); boards are staged as tile values in pinned host memory and flushed to the
+    device ring in batches (packed on the GPU), so sampling never touches Python objects.
+    ``len()`` and the oldest-first logical indexing match the deque the reference uses."""
+
+    STAGE = 2048
+
+    def __init__(self, iterable=(), maxlen=None, device="cuda"):
+        if maxlen is None:
+            raise ValueError("ReplayDeque needs a maxlen (the replay_buffer_length)")
+        self.maxlen = int(maxlen)
+        self.ring = ReplayRing(self.maxlen, device=device)
+        self._n_total = 0
+        self._h_s = torch.zeros((self.STAGE, 16), dtype=torch.int64).pin_memory()
+        self._h_s2 = torch.zeros((self.STAGE, 16), dtype=torch.int64).pin_memory()
+        self._h_a = torch.zeros(self.STAGE, dtype=torch.uint8).pin_memory()
+        self._h_r = torch.zeros(self.STAGE, dtype=torch.int32).pin_memory()
+        self._h_d = torch.zeros(self.STAGE, dtype=torch.uint8).pin_memory()
+        self._staged = 0
+        for item in iterable:
+            self.append(item)
+
+    def __len__(self) -> int:
+        return min(self._n_total, self.maxlen)
+
+    def append(self, experience) -> None:
+        board, action, reward, next_board, done = experience
+        i = self._staged
+        self._h_s[i] = torch.from_numpy(np.ascontiguousarray(board.state, dtype=np.int64).reshape(16))
+        self._h_s2[i] = torch.from_numpy(np.ascontiguousarray(next_board.state, dtype=np.int64).reshape(16))
+        self._h_a[i] = int(action)
+        self._h_r[i] = int(reward)
+        self._h_d[i] = int(bool(done))
+        self._staged += 1
+        self._n_total += 1
+        if self._staged == self.STAGE:
+            self.flush()
+
+    def flush(self) -> None:
+        """Upload the staged transitions: H2D of tile values, pack on the GPU, ring append."""
+        n = self._staged
+        if n == 0:
+            return
+        from . import env
+        dev = self.ring.device
+        with torch.cuda.device(dev):
+            s = env.pack(self._h_s[:n].to(dev, non_blocking=True))
+            s2 = env.pack(self._h_s2[:n].to(dev, non_blocking=True))
+            self.ring.append(s, self._h_a[:n].to(dev, non_blocking=True), self._h_r[:n].to(dev, non_blocking=True),
+                             s2, self._h_d[:n].to(dev, non_blocking=True))
+            torch.cuda.current_stream(dev).synchronize()     # staging buffers are reused
+        self._staged = 0
+
+    def sample(self, batch_size, indices=None, **kw):
+        self.flush()
+        idx = None
+        if indices is not None:
+            idx = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(self.ring.device)
+        return self.ring.sample(batch_size, idx_override=idx, **kw)

@@ -1,0 +1,90 @@
+"""Double-DQN updates at scale: GPU replay sampling (K2) + float64 Q-network forwards (torch) +
+fused target/loss (K3) + backward + gradient allreduce (NCCL) + Adam, captured in one CUDA graph.
+
+`DDQNUpdater.update()` is the "real" update (zero_grad -> backward -> allreduce -> step); the
+reference's train_step order, which never changes the weights, is what the drop-in
+`dqn_lib.train_step` reproduces by default.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from . import ddqn, dist as bdist
+from .replay import ReplayRing
+
+
+class DDQNUpdater:
+    def __init__(self, model: torch.nn.Module, ring: ReplayRing, batch_size: int = 5000, gamma: float = 0.8,
+                 lr: float = 1e-2, use_double: bool = True, conv: bool = True, target_model=None,
+                 use_graph: bool = True, seed: int = 2051):
+        self.model, self.ring = model, ring
+        self.target = target_model if target_model is not None else copy.deepcopy(model)
+        for p in self.target.parameters():
+            p.requires_grad_(False)
+        self.B, self.gamma, self.use_double, self.conv, self.seed = int(batch_size), float(gamma), use_double, conv, seed
+        self.device = next(model.parameters()).device
+        bdist.broadcast_module(self.model)
+        bdist.broadcast_module(self.target)
+        self.grads = bdist.FlatGrads(model)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, capturable=self.device.type == "cuda")
+        kw = dict(device=self.device)
+        B = self.B
+        self.batch = (torch.empty((B, 16), dtype=torch.float64, **kw), torch.empty(B, dtype=torch.int64, **kw),
+                      torch.empty(B, dtype=torch.int64, **kw), torch.empty((B, 16), dtype=torch.float64, **kw),
+                      torch.empty(B, dtype=torch.int64, **kw))
+        self.loss = torch.zeros((), dtype=torch.float64, **kw)
+        self.updates = 0
+        self.graph = None
+        self.use_graph = use_graph and self.device.type == "cuda"
+
+    def _shape(self, x):
+        return x.view(self.B, 1, 4, 4) if self.conv else x
+
+    def _update_eager(self):
+        states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
+                                                                        out=self.batch)
+        with torch.no_grad():
+            q_next_target = self.target(self._shape(next_states))
+            q_next_online = self.model(self._shape(next_states)) if self.use_double else None
+        q_cur = self.model(self._shape(states))
+        loss, _, _ = ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones, self.gamma,
+                                    self.use_double)
+        self.grads.zero_()
+        loss.backward()
+        self.grads.allreduce_()          # sum over ranks == gradient of the summed loss over the global batch
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def update(self) -> torch.Tensor:
+        """One update; returns the (device) loss tensor of this rank's batch."""
+        if not self.use_graph:
+            self._update_eager()
+        else:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        self.updates += 1
+        return self.loss
+
+    def _capture(self):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):           # warm-up on a side stream (allocator, cuDNN/cuBLAS plans, Adam state)
+                self._update_eager()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._update_eager()
+
+    def sync_target(self) -> None:
+        """target <- online (the reference's load_state_dict(deepcopy(...)), src/dqn_lib.py:227-228);
+        a local copy on every rank: the weights are already identical after the allreduce."""
+        with torch.no_grad():
+            for t, p in zip(self.target.parameters(), self.model.parameters()):
+                t.copy_(p)
+            for t, p in zip(self.target.buffers(), self.model.buffers()):
+                t.copy_(p)

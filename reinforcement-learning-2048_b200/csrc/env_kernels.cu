@@ -60,7 +60,7 @@ __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint3
   const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
     spawn_kth_empty(nlo, nhi, w, e29, one);
-  } else if (changed) {
+  } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
 }
@@ -261,6 +261,24 @@ __global__ void reset_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t 
   boards[i] = ((uint64_t)hi << 32) | lo;
 }
 
+__global__ void spawn_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t seed, uint64_t step,
+                             uint64_t index_base, uint32_t p4, const uint8_t* __restrict__ where_flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (where_flags && !(where_flags[i] & B2048_FLAG_CHANGED)) return;
+  const uint64_t bd = boards[i];
+  uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
+  const uint64_t g = index_base + (uint64_t)i;
+  const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
+  const uint32_t e = ((w << 16) < p4) ? 2u : 1u;
+  if (bd == 0) {
+    spawn_at(lo, hi, w >> 28, e);            // 16 empty cells: the prefix trick needs <= 15
+  } else {
+    spawn_kth_empty(lo, hi, w, e << 29);     // no empty cell -> nothing happens
+  }
+  boards[i] = ((uint64_t)hi << 32) | lo;
+}
+
 __global__ void pack_kernel(const int64_t* __restrict__ tiles, uint64_t* __restrict__ boards,
                             uint8_t* __restrict__ bad, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,6 +460,19 @@ extern "C" int b2048_reset(uint64_t* boards, int64_t n, uint64_t seed, uint64_t 
   B2048_CTX_OR_RETURN();
   (void)ctx;
   reset_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, n, seed, step, index_base, p4_threshold, where_flags);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_spawn(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step,
+                           uint64_t index_base, uint32_t p4_threshold, const uint8_t* where_flags,
+                           void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!boards) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  spawn_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       boards, n, seed, step, index_base, p4_threshold, where_flags);
   return (int)cudaGetLastError();
 }

@@ -47,6 +47,7 @@ __global__ void ring_sample_kernel(b2048_ring ring, int64_t B, uint64_t seed, ui
   const int c = (int)(t & 15);
   if (j >= B) return;
   const int64_t head = ring.head_size[0], size = ring.head_size[1];
+  if (ctr == B2048_CTR_AUTO) ctr = (uint64_t)ring.head_size[2];
   int64_t idx;
   if (idx_override) {
     idx = idx_override[j];
@@ -71,6 +72,10 @@ __global__ void ring_sample_kernel(b2048_ring ring, int64_t B, uint64_t seed, ui
     dones[j] = ring.d[slot];
     if (idx_out) idx_out[j] = idx;
   }
+}
+
+__global__ void ring_bump_kernel(b2048_ring ring) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ring.head_size[2] += 1;
 }
 
 }  // namespace
@@ -112,5 +117,8 @@ extern "C" int replay_sample(const b2048_ring* ring, int64_t B, uint64_t seed, u
   const int64_t threads = B * 16;
   ring_sample_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
       *ring, B, seed, ctr, idx_override, states, next_states, actions, rewards, dones, idx_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || ctr != B2048_CTR_AUTO) return (int)e;
+  ring_bump_kernel<<<1, 32, 0, st>>>(*ring);
   return (int)cudaGetLastError();
 }
