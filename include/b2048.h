@@ -160,8 +160,8 @@ typedef struct b2048_ring {
 } b2048_ring;
 
 /* Append n transitions in order (oldest first); if n > capacity only the last `capacity` survive,
- * like deque(maxlen).  `done_flags` holds step flags bytes or 0/1 values: done = (byte & 0x10) or
- * (byte == 1). */
+ * like deque(maxlen).  `done_flags` holds the step kernel's flags bytes: done = byte & 0x10
+ * (B2048_FLAG_DONE); every other bit is ignored. */
 int replay_append(const b2048_ring* ring, const uint64_t* s, const uint8_t* a, const int32_t* r,
                   const uint64_t* s2, const uint8_t* done_flags, int64_t n, void* stream);
 

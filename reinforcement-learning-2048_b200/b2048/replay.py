@@ -38,9 +38,12 @@ class ReplayRing:
     def __len__(self) -> int:          # synchronises (reads the device counter)
         return int(self.head_size[1].item())
 
-    def append(self, s, a, r, s2, done_flags) -> None:
-        """Append n transitions (src/dqn_lib.py:106).  `done_flags`: step flags bytes or 0/1."""
+    def append(self, s, a, r, s2, done_flags, done_is_bool: bool = False) -> None:
+        """Append n transitions (src/dqn_lib.py:106).  `done_flags`: the step kernel's flags bytes
+        (done = byte & 0x10); pass done_is_bool=True for a 0/1 array."""
         n = s.numel()
+        if done_is_bool:
+            done_flags = (done_flags != 0).to(torch.uint8) * 0x10
         _chk(s, torch.int64, name="s"); _chk(s2, torch.int64, n, "s2"); _chk(a, torch.uint8, n, "a")
         _chk(r, torch.int32, n, "r"); _chk(done_flags, torch.uint8, n, "done")
         with torch.cuda.device(self._dev):
@@ -111,7 +114,7 @@ class ReplayDeque:
         self._h_s2[i] = torch.from_numpy(np.ascontiguousarray(next_board.state, dtype=np.int64).reshape(16))
         self._h_a[i] = int(action)
         self._h_r[i] = int(reward)
-        self._h_d[i] = int(bool(done))
+        self._h_d[i] = 0x10 if bool(done) else 0            # B2048_FLAG_DONE
         self._staged += 1
         self._n_total += 1
         if self._staged == self.STAGE:

@@ -23,8 +23,7 @@ __global__ void ring_append_kernel(b2048_ring ring, const uint64_t* __restrict__
   ring.s2[slot] = s2[i];
   ring.r[slot] = r[i];
   ring.a[slot] = a[i] & 3u;
-  const uint8_t f = done_flags[i];
-  ring.d[slot] = ((f & B2048_FLAG_DONE) || f == 1) ? 1 : 0;
+  ring.d[slot] = (done_flags[i] & B2048_FLAG_DONE) ? 1 : 0;
 }
 
 __global__ void ring_advance_kernel(b2048_ring ring, int64_t n) {

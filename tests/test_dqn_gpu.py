@@ -28,7 +28,7 @@ def fill_ring(d, cuda, capacity=None):
     ring = b2048.ReplayRing(capacity or n, device=cuda)
     ring.append(dev_boards(d["buf_state"], cuda), torch.from_numpy(d["buf_action"]).to(cuda),
                 torch.from_numpy(d["buf_reward"].astype(np.int32)).to(cuda), dev_boards(d["buf_next"], cuda),
-                torch.from_numpy(d["buf_done"]).to(cuda))
+                torch.from_numpy(d["buf_done"]).to(cuda), done_is_bool=True)
     return ring
 
 
@@ -58,7 +58,7 @@ def test_replay_ring_wraps_like_deque(cuda, dq):
     cuts = [0, 1, 300, 999, 1000, 1700, n - 1500, n]           # last piece is 1500 > capacity
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         ring.append(s[lo:hi].contiguous(), a[lo:hi].contiguous(), r[lo:hi].contiguous(), s2[lo:hi].contiguous(),
-                    dn[lo:hi].contiguous())
+                    dn[lo:hi].contiguous(), done_is_bool=True)
         assert len(ring) == min(hi, cap)
     idx = torch.arange(cap, device=cuda)
     st, ac, rw, ns, dd = ring.sample(cap, idx_override=idx)
@@ -84,7 +84,7 @@ def test_replay_philox_sampling_is_uniform_and_reproducible(cuda, dq):
     ring2 = b2048.ReplayRing(16, device=cuda)
     z = torch.zeros(4, dtype=torch.int64, device=cuda)
     ring2.append(z, torch.zeros(4, dtype=torch.uint8, device=cuda), torch.zeros(4, dtype=torch.int32, device=cuda), z,
-                 torch.tensor([0x0F, 0x10, 0x2F, 0x30], dtype=torch.uint8, device=cuda))
+                 torch.tensor([0x01, 0x10, 0x2F, 0x30], dtype=torch.uint8, device=cuda))
     assert ring2.sample(4, idx_override=torch.arange(4, device=cuda))[4].tolist() == [0, 1, 0, 1]
 
 
