@@ -168,6 +168,78 @@ def cpu_baseline_sample():
                       f"({dt:.1f} s wall, {threads} pthreads, oracle/board_oracle.c)"}
 
 
+def conv_qnet():
+    from torch import nn   # reference configs/double_dqn_conv.py:19-28 (33 476 parameters, float64)
+    return nn.Sequential(nn.Conv2d(1, 64, kernel_size=2), nn.ReLU(), nn.Conv2d(64, 64, kernel_size=2), nn.ReLU(),
+                         nn.Flatten(), nn.Linear(2 * 2 * 64, 64), nn.ReLU(), nn.Linear(64, 4)).double()
+
+
+def dense_qnet():
+    from torch import nn   # reference configs/double_dqn_dense.py:7-15 (403 716 parameters, float64)
+    return nn.Sequential(nn.Linear(16, 512), nn.ReLU(), nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, 256),
+                         nn.ReLU(), nn.Linear(256, 4)).double()
+
+
+def secondary_metrics(args, dev, rank, world, barrier):
+    """The other numbers BASELINE.json asks for, reported beside the headline (not the roofline
+    kernel): config 2 (1Mi boards x 4 actions, L2-resident), DDQN updates/sec at batch 5000 for the
+    conv and dense Q-networks (real updates: sample -> 3 forwards -> fused target/loss -> backward
+    -> NCCL allreduce -> Adam, one CUDA graph), and a random-policy rollout with replay append."""
+    import torch
+    import torch.distributed as dist
+    import b2048
+    from b2048 import env
+    from b2048.rollout import VectorEnv
+    from b2048.trainer import DDQNUpdater
+
+    def timed(fn, iters):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / iters
+
+    out = {}
+    n2 = 1 << 20
+    b2 = env.random_boards(n2, seed=SEED_BOARDS, index_base=rank * n2, device=dev)
+    o2 = (torch.empty((n2, 4), dtype=torch.int64, device=dev), torch.empty((n2, 4), dtype=torch.int32, device=dev),
+          torch.empty(n2, dtype=torch.uint8, device=dev))
+    for w in range(3):
+        env.step_all4(b2, seed=SEED_SPAWN, step_index=w, index_base=rank * n2, out=o2)
+    ms = timed(lambda i: env.step_all4(b2, seed=SEED_SPAWN, step_index=3 + i, index_base=rank * n2, out=o2), 50)
+    out["config2_all4"] = {"workload": "1Mi random boards x 4 actions per GPU (57 MB/launch: L2-resident, not a roofline run)",
+                           "board_actions_per_sec": world * 4 * n2 / (ms * 1e-3), "ms_per_launch": ms,
+                           "algorithmic_GBps": n2 * 57 / (ms * 1e-3) / 1e9}
+
+    # rollout: random policy incl. legal mask, replay append and masked reset (5 launches + torch bookkeeping / step)
+    nv = 1 << 22
+    ve = VectorEnv(nv, device=dev, seed=3, index_base=rank * nv)
+    ring = b2048.ReplayRing(15000, device=dev)
+    for _ in range(3):
+        ve.step(replay=ring)
+    ms = timed(lambda i: ve.step(replay=ring), 20)
+    out["rollout_random_policy"] = {"workload": "4Mi concurrent games per GPU, random policy, replay ring 15000, auto-reset",
+                                    "env_steps_per_sec": world * nv / (ms * 1e-3), "ms_per_step": ms}
+
+    for name, net, conv in (("conv", conv_qnet, True), ("dense", dense_qnet, False)):
+        torch.manual_seed(0)
+        up = DDQNUpdater(net().to(dev), ring, batch_size=5000, gamma=0.8, lr=1e-2, conv=conv, use_graph=True)
+        for _ in range(3):
+            up.update()
+        ms = timed(lambda i: up.update(), 100)
+        out[f"ddqn_updates_{name}"] = {
+            "workload": f"{name} Q-net float64, batch 5000/GPU, replay 15000, gamma 0.8 (f32), Double DQN, Adam; "
+                        "sample+3 fwd+fused loss+bwd+allreduce+Adam in one CUDA graph",
+            "updates_per_sec": 1e3 / ms, "ms_per_update": ms, "global_batch": 5000 * world}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -228,6 +300,8 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True
 
+    extra = secondary_metrics(args, dev, rank, world, barrier)
+
     times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -256,6 +330,7 @@ def run_ours(args):
                          "kernel": "step_stream_kernel<false>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "peak_source": peak_src},
         }
+        line["extra"] = extra
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)

@@ -12,6 +12,7 @@ import copy
 import torch
 
 from . import ddqn, dist as bdist
+from .qnet import accelerate
 from .replay import ReplayRing
 
 
@@ -25,6 +26,8 @@ class DDQNUpdater:
             p.requires_grad_(False)
         self.B, self.gamma, self.use_double, self.conv, self.seed = int(batch_size), float(gamma), use_double, conv, seed
         self.device = next(model.parameters()).device
+        # same parameter tensors, convolutions evaluated as float64 GEMMs (see qnet.py)
+        self.f_model, self.f_target = accelerate(self.model), accelerate(self.target)
         bdist.broadcast_module(self.model)
         bdist.broadcast_module(self.target)
         self.grads = bdist.FlatGrads(model)
@@ -46,9 +49,9 @@ class DDQNUpdater:
         states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
                                                                         out=self.batch)
         with torch.no_grad():
-            q_next_target = self.target(self._shape(next_states))
-            q_next_online = self.model(self._shape(next_states)) if self.use_double else None
-        q_cur = self.model(self._shape(states))
+            q_next_target = self.f_target(self._shape(next_states))
+            q_next_online = self.f_model(self._shape(next_states)) if self.use_double else None
+        q_cur = self.f_model(self._shape(states))
         loss, _, _ = ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones, self.gamma,
                                     self.use_double)
         self.grads.zero_()

@@ -30,6 +30,7 @@ import torch
 from board import Board2048
 from b2048 import ddqn as _ddqn
 from b2048 import env as _env
+from b2048.qnet import accelerate as _accelerate
 from b2048.replay import ReplayDeque
 
 FIX_UPDATE_ORDER = os.environ.get("B2048_FIX_UPDATE_ORDER", "0") == "1"
@@ -173,9 +174,11 @@ def train_step(batch_size: int, discount_factor, model, target_model, replay_buf
         batch_size, replay_buffer, device, board_to_tensor_function, extract_samples_function)
     dev = _cuda_device(device)
     on_dev = states.device == dev
-    q_next_target = target_model(next_states)
-    q_next_online = model(next_states) if use_double_dqn else None
-    q_cur = model(states)
+    # same parameters; 2x2 convolutions are evaluated as float64 GEMMs (b2048/qnet.py)
+    f_model, f_target = _accelerate(model), _accelerate(target_model)
+    q_next_target = f_target(next_states)
+    q_next_online = f_model(next_states) if use_double_dqn else None
+    q_cur = f_model(states)
     if on_dev and _is_sum_mse(loss_fn) and q_cur.dtype == torch.float64:
         loss, _, _ = _ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones,
                                      discount_factor, use_double_dqn)

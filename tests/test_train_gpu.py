@@ -132,3 +132,22 @@ def test_updater_graph_equals_eager_and_learns(cuda):
     assert not any(torch.equal(p, q) for p, q in zip(c.model.parameters(), base.parameters()))
     c.sync_target()
     assert all(torch.equal(p, q) for p, q in zip(c.model.parameters(), c.target.parameters()))
+
+
+def test_fast_conv_forward_equals_cudnn_path(cuda):
+    """Conv2d layers evaluated as float64 GEMMs: same outputs and gradients as nn.Conv2d (1e-12)."""
+    from b2048.qnet import accelerate
+    torch.manual_seed(3)
+    net = conv_model().to(cuda)
+    fast = accelerate(net)
+    assert fast is not net and accelerate(dense_model()) .__class__.__name__ == "Sequential"
+    x = torch.randint(0, 12, (5000, 1, 4, 4), device=cuda).double()
+    a, b = net(x), fast(x)
+    np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().cpu().numpy(), rtol=1e-12, atol=1e-13)
+    a.square().sum().backward()
+    g1 = [p.grad.clone() for p in net.parameters()]
+    for p in net.parameters():
+        p.grad = None
+    fast(x).square().sum().backward()
+    for u, p in zip(g1, net.parameters()):
+        np.testing.assert_allclose(p.grad.cpu().numpy(), u.cpu().numpy(), rtol=1e-10, atol=1e-10 * float(u.abs().max()))
