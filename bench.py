@@ -285,6 +285,15 @@ def run_ours(args):
     if rank == 0:
         clocks = sampler.summary(t_wall0, t_wall1)
 
+    if args.headline_only:
+        sampler.stop_flag = True
+        if rank == 0:
+            print(json.dumps({"metric": "env_steps_per_sec", "value": world * n * args.steps / (total_ms * 1e-3),
+                              "ms_per_step": total_ms / args.steps, "headline_only": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----------------------
     hb, ha = boards.cpu().pin_memory(), actions.cpu().pin_memory()
     hn = torch.empty(n, dtype=torch.int64).pin_memory()
@@ -344,6 +353,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--headline-only", action="store_true",
+                    help="only the device-resident env-step timing (for ncu launch lists); no e2e / extras / CPU baseline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                       # timing rule: at least 3 warm-up steps

@@ -120,6 +120,21 @@ int b2048_reset(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step, uint6
 int b2048_spawn(uint64_t* boards, int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
                 uint32_t p4_threshold, const uint8_t* where_flags, void* stream);
 
+/* Per-game bookkeeping of a batched rollout, fused with the episode auto-reset (the fields the
+ * reference hands to Experiment.add_episode, src/experiments.py:112-122, kept on the device).
+ * For every board i, after b2048_step produced (next, reward, flags) from `prev`:
+ *   ep_score[i] += reward[i]; ep_moves[i] += 1; ep_qsum[i] += max_q[i] (if max_q != NULL);
+ *   if flags[i] & DONE: totals {games, sum of merge scores, sum of moves, sum of mean max-Q} and
+ *   max_tile_hist[exponent of the largest tile of prev[i]] are updated, the accumulators are
+ *   cleared and next[i] is replaced by a fresh board (zeros + two spawns, as b2048_reset).
+ * totals: device int64[4] {games, score_sum, moves_sum, reserved}; qmean_sum: device double[1];
+ * max_tile_hist: device int64[16].  All accumulators are caller-allocated and zero-initialised. */
+int b2048_episode_end(uint64_t* next, const uint64_t* prev, const int32_t* reward,
+                      const uint8_t* flags, const double* max_q, int64_t* ep_score, int32_t* ep_moves,
+                      double* ep_qsum, int64_t* totals, double* qmean_sum, int64_t* max_tile_hist,
+                      int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
+                      uint32_t p4_threshold, void* stream);
+
 /* int64 tiles [n,16] (reference `state`, row-major) <-> packed boards.  bad[i] (nullable) is set
  * to 1 if a tile is not 0 or a power of two in 2..32768. */
 int b2048_pack(const int64_t* tiles, uint64_t* boards, uint8_t* bad, int64_t n, void* stream);

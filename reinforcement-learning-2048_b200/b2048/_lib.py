@@ -37,6 +37,7 @@ SIGNATURES = {
     "b2048_legal_mask": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "b2048_reset": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p]),
     "b2048_spawn": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p]),
+    "b2048_episode_end": (c_int, [c_void_p] * 11 + [c_int64, c_uint64, c_uint64, c_uint64, c_uint32, c_void_p]),
     "b2048_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2048_unpack_tiles": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "b2048_unpack_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -139,6 +139,28 @@ def spawn(boards, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT, where_f
     return boards
 
 
+def episode_end(nxt, prev, reward, flags, max_q, ep_score, ep_moves, ep_qsum, totals, qmean_sum, max_tile_hist,
+                seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT):
+    """Fused per-game bookkeeping + auto-reset of finished games (b2048_episode_end)."""
+    n = nxt.numel()
+    dev = _dev(nxt)
+    _lib.init(dev)
+    _chk(nxt, torch.int64, n, "next"); _chk(prev, torch.int64, n, "prev"); _chk(reward, torch.int32, n, "reward")
+    _chk(flags, torch.uint8, n, "flags"); _chk(ep_score, torch.int64, n, "ep_score")
+    _chk(ep_moves, torch.int32, n, "ep_moves"); _chk(totals, torch.int64, 4, "totals")
+    _chk(max_tile_hist, torch.int64, 16, "max_tile_hist")
+    if max_q is not None:
+        _chk(max_q, torch.float64, n, "max_q")
+    if ep_qsum is not None:
+        _chk(ep_qsum, torch.float64, n, "ep_qsum"); _chk(qmean_sum, torch.float64, 1, "qmean_sum")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b2048_episode_end(_ptr(nxt), _ptr(prev), _ptr(reward), _ptr(flags), _ptr(max_q),
+                                                _ptr(ep_score), _ptr(ep_moves), _ptr(ep_qsum), _ptr(totals),
+                                                _ptr(qmean_sum), _ptr(max_tile_hist), n, seed & _U64,
+                                                step_index & _U64, index_base & _U64, p4, _stream(nxt)),
+                   "b2048_episode_end")
+
+
 def new_boards(n, device="cuda", **kw):
     return reset(torch.empty(n, dtype=torch.int64, device=device), **kw)
 

@@ -31,14 +31,12 @@ class VectorEnv:
         self.actions = torch.empty(self.n, dtype=torch.uint8, **kw)
         self.max_q = torch.empty(self.n, dtype=torch.float64, **kw)
         self.obs = torch.empty((self.n, 16), dtype=torch.float64, **kw)
-        # per-game accumulators
+        # per-game accumulators and totals over finished games (all on the device)
         self.ep_score = torch.zeros(self.n, dtype=torch.int64, **kw)
-        self.ep_moves = torch.zeros(self.n, dtype=torch.int64, **kw)
+        self.ep_moves = torch.zeros(self.n, dtype=torch.int32, **kw)
         self.ep_qsum = torch.zeros(self.n, dtype=torch.float64, **kw)
-        # totals over finished games
-        self.finished = torch.zeros((), dtype=torch.int64, **kw)
-        self.sum_score = torch.zeros((), dtype=torch.int64, **kw)
-        self.sum_moves = torch.zeros((), dtype=torch.int64, **kw)
+        self.totals = torch.zeros(4, dtype=torch.int64, **kw)          # games, merge-score sum, moves sum
+        self.qmean_sum = torch.zeros(1, dtype=torch.float64, **kw)     # sum over games of mean max-Q
         self.max_tile_hist = torch.zeros(16, dtype=torch.int64, **kw)
 
     def observe(self) -> torch.Tensor:
@@ -51,12 +49,12 @@ class VectorEnv:
         """One step of every game.  model=None or epsilon>=1 plays the uniformly random policy of
         the reference's epsilon branch (illegal no-op moves included, src/dqn_lib.py:20-21)."""
         self.t += 1
-        env.legal_mask(self.boards, out=self.legal)
-        if model is not None and epsilon < 1.0:
+        greedy = model is not None and epsilon < 1.0
+        if greedy:
+            env.legal_mask(self.boards, out=self.legal)
             q = model(self.observe()).contiguous()
             ddqn.egreedy_select(q, self.legal, epsilon, seed=self.seed ^ 0x5EED, ctr=self.t,
                                 index_base=self.index_base, out=(self.actions, self.max_q))
-            self.ep_qsum += self.max_q
         else:
             env.random_actions(self.n, seed=self.seed ^ 0xAC71, step_index=self.t, index_base=self.index_base,
                                out=self.actions)
@@ -64,27 +62,17 @@ class VectorEnv:
                  p4=self.p4, out=(self.next_boards, self.reward, self.flags))
         if replay is not None:
             replay.append(self.boards, self.actions, self.reward, self.next_boards, self.flags)
-        done = (self.flags & env.FLAG_DONE) != 0
-        self.ep_score += self.reward
-        self.ep_moves += 1
-        # finished games: fold their statistics into the totals, then start fresh boards
-        nd = done.sum()
-        self.finished += nd
-        self.sum_score += torch.where(done, self.ep_score, 0).sum()
-        self.sum_moves += torch.where(done, self.ep_moves, 0).sum()
-        shifts = 4 * torch.arange(16, device=self.device, dtype=torch.int64)
-        max_exp = ((self.boards[:, None] >> shifts) & 0xF).amax(dim=1)
-        self.max_tile_hist += torch.bincount(max_exp[done], minlength=16)[:16]
-        self.ep_score.masked_fill_(done, 0)
-        self.ep_moves.masked_fill_(done, 0)
-        self.ep_qsum.masked_fill_(done, 0.0)
+        # one fused pass: per-game accumulators, totals of finished games, fresh boards for them
+        env.episode_end(self.next_boards, self.boards, self.reward, self.flags, self.max_q if greedy else None,
+                        self.ep_score, self.ep_moves, self.ep_qsum, self.totals, self.qmean_sum,
+                        self.max_tile_hist, seed=self.seed ^ 0x4E57, step_index=self.t, index_base=self.index_base,
+                        p4=self.p4)
         self.boards, self.next_boards = self.next_boards, self.boards
-        env.reset(self.boards, seed=self.seed ^ 0x4E57, step_index=self.t, index_base=self.index_base, p4=self.p4,
-                  where_flags=self.flags)
         return self.flags
 
     def stats(self) -> dict:
-        f = int(self.finished.item())
+        games, score, moves, _ = self.totals.tolist()
         hist = {int(2 ** e): int(c) for e, c in enumerate(self.max_tile_hist.tolist()) if c}
-        return {"games": f, "mean_merge_score": float(self.sum_score.item()) / max(f, 1),
-                "mean_moves": float(self.sum_moves.item()) / max(f, 1), "max_tile_hist": hist, "steps": self.t * self.n}
+        return {"games": games, "mean_merge_score": score / max(games, 1), "mean_moves": moves / max(games, 1),
+                "mean_max_q": float(self.qmean_sum.item()) / max(games, 1), "max_tile_hist": hist,
+                "steps": self.t * self.n}

@@ -245,20 +245,22 @@ __global__ void legal_mask_kernel(const uint64_t* __restrict__ boards, uint8_t* 
   flags[i] = (uint8_t)(m | (m ? 0u : B2048_FLAG_DONE));
 }
 
+__device__ __forceinline__ uint64_t fresh_board(uint64_t seed, uint64_t step, uint64_t g, uint32_t p4) {
+  const uint4 r = philox_at(seed, DOM_RESET, g, step);
+  uint32_t lo = 0, hi = 0;
+  spawn_at(lo, hi, r.x >> 28, (r.y < p4) ? 2u : 1u);
+  spawn_kth_empty(lo, hi, r.z, (r.w < p4) ? (2u << 29) : (1u << 29));
+  return ((uint64_t)hi << 32) | lo;
+}
+
 __global__ void reset_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t seed, uint64_t step,
                              uint64_t index_base, uint32_t p4,
                              const uint8_t* __restrict__ where_flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (where_flags && !(where_flags[i] & B2048_FLAG_DONE)) return;
-  const uint4 r = philox_at(seed, DOM_RESET, index_base + (uint64_t)i, step);
   // first spawn: uniform over 16 cells; second: uniform over the remaining 15 (row-major rank)
-  const uint32_t c1 = r.x >> 28;
-  const uint32_t e1 = (r.y < p4) ? 2u : 1u;
-  uint32_t lo = 0, hi = 0;
-  spawn_at(lo, hi, c1, e1);
-  spawn_kth_empty(lo, hi, r.z, (r.w < p4) ? (2u << 29) : (1u << 29));
-  boards[i] = ((uint64_t)hi << 32) | lo;
+  boards[i] = fresh_board(seed, step, index_base + (uint64_t)i, p4);
 }
 
 __global__ void spawn_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t seed, uint64_t step,
@@ -277,6 +279,67 @@ __global__ void spawn_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t 
     spawn_kth_empty(lo, hi, w, e << 29);     // no empty cell -> nothing happens
   }
   boards[i] = ((uint64_t)hi << 32) | lo;
+}
+
+// Episode bookkeeping + auto-reset in one pass (see b2048_episode_end in include/b2048.h).
+// Finished games are rare (~1 % of boards per step), so their totals go through warp-aggregated
+// atomics: one atomic per warp and counter instead of one per finished game.
+__global__ void episode_end_kernel(uint64_t* __restrict__ next, const uint64_t* __restrict__ prev,
+                                   const int32_t* __restrict__ reward, const uint8_t* __restrict__ flags,
+                                   const double* __restrict__ max_q, int64_t* __restrict__ ep_score,
+                                   int32_t* __restrict__ ep_moves, double* __restrict__ ep_qsum,
+                                   unsigned long long* __restrict__ totals, double* __restrict__ qmean_sum,
+                                   unsigned long long* __restrict__ hist, int64_t n, uint64_t seed,
+                                   uint64_t step, uint64_t index_base, uint32_t p4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  bool done = false;
+  int64_t score = 0;
+  int32_t moves = 0;
+  double qmean = 0.0;
+  uint32_t top = 0;
+  if (valid) {
+    score = ep_score[i] + reward[i];
+    moves = ep_moves[i] + 1;
+    double qs = ep_qsum ? ep_qsum[i] + (max_q ? max_q[i] : 0.0) : 0.0;
+    done = (flags[i] & B2048_FLAG_DONE) != 0;
+    if (done) {
+      uint64_t b = prev[i];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) top = max(top, (uint32_t)(b >> (4 * c)) & 0xFu);
+      qmean = qs / (double)moves;
+      next[i] = fresh_board(seed, step, index_base + (uint64_t)i, p4);
+      ep_score[i] = 0;
+      ep_moves[i] = 0;
+      if (ep_qsum) ep_qsum[i] = 0.0;
+    } else {
+      ep_score[i] = score;
+      ep_moves[i] = moves;
+      if (ep_qsum) ep_qsum[i] = qs;
+    }
+  }
+  const unsigned mask = __ballot_sync(0xFFFFFFFFu, done);
+  if (mask == 0) return;
+  // warp-level sums over the finished games of this warp
+  unsigned long long s_score = done ? (unsigned long long)score : 0ull, s_moves = done ? (unsigned long long)moves : 0ull;
+  double s_q = done ? qmean : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_score += __shfl_down_sync(0xFFFFFFFFu, s_score, o);
+    s_moves += __shfl_down_sync(0xFFFFFFFFu, s_moves, o);
+    s_q += __shfl_down_sync(0xFFFFFFFFu, s_q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&totals[0], (unsigned long long)__popc(mask));
+    atomicAdd(&totals[1], s_score);
+    atomicAdd(&totals[2], s_moves);
+    if (qmean_sum) atomicAdd(qmean_sum, s_q);
+  }
+  if (done) {
+    // one atomic per distinct max tile in the warp
+    const unsigned peers = __match_any_sync(mask, top);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[top], (unsigned long long)__popc(peers));
+  }
 }
 
 __global__ void pack_kernel(const int64_t* __restrict__ tiles, uint64_t* __restrict__ boards,
@@ -474,6 +537,23 @@ extern "C" int b2048_spawn(uint64_t* boards, int64_t n, uint64_t seed, uint64_t 
   (void)ctx;
   spawn_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       boards, n, seed, step, index_base, p4_threshold, where_flags);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2048_episode_end(uint64_t* next, const uint64_t* prev, const int32_t* reward,
+                                 const uint8_t* flags, const double* max_q, int64_t* ep_score,
+                                 int32_t* ep_moves, double* ep_qsum, int64_t* totals, double* qmean_sum,
+                                 int64_t* max_tile_hist, int64_t n, uint64_t seed, uint64_t step,
+                                 uint64_t index_base, uint32_t p4_threshold, void* stream) {
+  if (n < 0) return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  if (!next || !prev || !reward || !flags || !ep_score || !ep_moves || !totals || !max_tile_hist) return B2048_EINVAL;
+  B2048_CTX_OR_RETURN();
+  (void)ctx;
+  episode_end_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      next, prev, reward, flags, max_q, ep_score, ep_moves, ep_qsum,
+      reinterpret_cast<unsigned long long*>(totals), qmean_sum,
+      reinterpret_cast<unsigned long long*>(max_tile_hist), n, seed, step, index_base, p4_threshold);
   return (int)cudaGetLastError();
 }
 
