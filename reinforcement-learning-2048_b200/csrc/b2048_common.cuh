@@ -263,13 +263,14 @@ __device__ __forceinline__ void lookup4_global(uint32_t zl, uint32_t zh, const u
   extra = ((i0 == 0xEEEEu) + (i1 == 0xEEEEu) + (i2 == 0xEEEEu) + (i3 == 0xEEEEu)) * 65536u;
 }
 // out-of-line copy for the rare miss of the shared-memory table (keeps the hot loop small)
-static __device__ __noinline__ uint4 lookup4_global_cold(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut,
-                                                         uint32_t* extra) {
-  uint4 e;
-  uint32_t x;
-  lookup4_global(zl, zh, glut, e.x, e.y, e.z, e.w, x);
-  *extra = x;
-  return e;
+static __device__ __noinline__ uint4 lookup4_global_cold(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut) {
+  return make_uint4(__ldg(glut + (zl & 0xFFFFu)), __ldg(glut + (zl >> 16)), __ldg(glut + (zh & 0xFFFFu)),
+                    __ldg(glut + (zh >> 16)));
+}
+// 65536 for every transformed row equal to 0xEEEE (its reward does not fit the table's 14 bits)
+__device__ __forceinline__ uint32_t extra_reward_eeee(uint32_t zl, uint32_t zh) {
+  return (((zl & 0xFFFFu) == 0xEEEEu) + ((zl >> 16) == 0xEEEEu) + ((zh & 0xFFFFu) == 0xEEEEu) +
+          ((zh >> 16) == 0xEEEEu)) * 65536u;
 }
 template <bool SMEM>
 __device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t* slut,
@@ -278,8 +279,9 @@ __device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t
   if (SMEM) {
     const uint32_t mx = __vmaxu2(zl, zh);
     if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
-      const uint4 e = lookup4_global_cold(zl, zh, glut, &extra);
+      const uint4 e = lookup4_global_cold(zl, zh, glut);
       e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
+      extra = extra_reward_eeee(zl, zh);
     } else {
       e0 = lut_at(slut, (zl * 4u) & 0x3FFFCu);
       e1 = lut_at(slut, __byte_perm(zl, 0u, 0x4432) * 4u);   // PRMT + shift-add: one ALU op less than SHF + LOP3

@@ -56,10 +56,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
 template <bool HAS_OVERRIDE>
 __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
-                                             uint32_t p4, uint32_t ovr, uint32_t& flags, uint32_t one = 1u) {
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
   const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w, e29, one);
+    spawn_kth_empty(nlo, nhi, w, e29);
   } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
@@ -71,7 +71,89 @@ __device__ __forceinline__ uint32_t pick_word(const uint4& r, uint32_t j) {
 }
 
 constexpr int STREAM_THREADS = 1024;
-constexpr int STREAM_SMEM_BYTES = LUT_SMEM_BYTES + (int)sizeof(SmemTabs) + 16;  // row table + small tables + mbarrier
+
+// Shared-memory map of the streaming kernel (byte offsets from the start of dynamic smem).  All
+// table reads use explicit shared-space loads on a 32-bit base address computed once: with generic
+// pointers ptxas re-derived the shared window base (S2R + MOV + LEA) for every board.
+constexpr uint32_t SM_ACT = (uint32_t)LUT_SMEM_BYTES;   // 4 rows x 32 B: per-action transform constants
+constexpr uint32_t SM_LEGAL = SM_ACT + 128;             // 4 rows x 32 B: flags byte per (action, frame mask)
+constexpr uint32_t SM_BAR = SM_LEGAL + 128;             // mbarrier
+constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// One board of the streaming kernel.  `sa` = shared base + 32 * action (row of both small tables).
+// Same arithmetic as slide_board<true> + finish_board (b2048_common.cuh), specialised for the
+// shared-memory map above; the flags byte incl. CHANGED comes straight from the legal table.
+template <bool HAS_OVERRIDE>
+__device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const uint32_t* __restrict__ glut,
+                                             uint32_t lo, uint32_t hi, uint32_t w, uint32_t p4, uint32_t ovr,
+                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags) {
+  const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
+  const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
+  uint32_t zl = __byte_perm(lo, hi, xa.x);
+  uint32_t zh = __byte_perm(lo, hi, xa.y);
+  {
+    const uint32_t tl = (zl ^ (zl >> xb.y)) & xb.z, th = (zh ^ (zh >> xb.y)) & xb.z;
+    zl ^= tl ^ (tl * xb.x);
+    zh ^= th ^ (th * xb.x);
+  }
+  uint32_t e0, e1, e2, e3, extra = 0;
+  const uint32_t mx = __vmaxu2(zl, zh);
+  if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
+    const uint4 e = lookup4_global_cold(zl, zh, glut);
+    e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
+    extra = extra_reward_eeee(zl, zh);
+  } else {
+    e0 = lds32(sbase + ((zl * 4u) & 0x3FFFCu));
+    e1 = lds32(sbase + __byte_perm(zl, 0u, 0x4432) * 4u);
+    e2 = lds32(sbase + ((zh * 4u) & 0x3FFFCu));
+    e3 = lds32(sbase + __byte_perm(zh, 0u, 0x4432) * 4u);
+  }
+  uint32_t wl = (e0 & 0xFFFFu) + (e1 << 16);
+  uint32_t wh = (e2 & 0xFFFFu) + (e3 << 16);
+  const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
+  const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
+  const uint32_t fl = h01 | h23;
+  const uint32_t s = (h01 & 0x3FFF3FFFu) + (h23 & 0x3FFF3FFFu);
+  reward = __dp2a_lo(s, 0x0404u, extra);
+
+  // legality of the input board in the transformed frame (see slide_board)
+  const uint32_t changed = (wl ^ zl) | (wh ^ zh);
+  const uint32_t n_l = nz3(zl), n_h = nz3(zh);
+  const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = zh >> 16;
+  const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
+  const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = n_h >> 16;
+  const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
+  const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
+  const uint32_t m = (changed ? 1u : 0u) + ((fl & 0x40004000u) ? 2u : 0u) + (up ? 4u : 0u) +
+                     ((dn_l | (dn_h & 0x0000FFFFu)) ? 8u : 0u);
+  flags = lds8(sa + m + SM_LEGAL);             // legal | DONE | CHANGED
+  if (fl & 0x80008000u) flags |= B2048_FLAG_OVERFLOW;
+
+  {
+    const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
+    wl ^= tl ^ (tl * xb.x);
+    wh ^= th ^ (th * xb.x);
+  }
+  olo = __byte_perm(wl, wh, xa.z);
+  ohi = __byte_perm(wl, wh, xa.w);
+  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags);
+}
 
 // ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
 // Requires 16-byte aligned boards/next/reward, 4-byte aligned actions/flags/override and n % 4 == 0
@@ -84,15 +166,25 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                        const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
                        uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
-  SmemTabs* tabs = reinterpret_cast<SmemTabs*>(smem_raw + LUT_SMEM_BYTES);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LUT_SMEM_BYTES + sizeof(SmemTabs));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM_BAR);
+  uint32_t sbase;   // shared-space base address, made opaque so that it lives in one register
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  fill_tabs(tabs);
+  if (threadIdx.x < 4) {
+    const ActXform x = act_xform((int)threadIdx.x);
+    uint32_t* row = reinterpret_cast<uint32_t*>(smem_raw + SM_ACT + 32 * threadIdx.x);
+    row[0] = x.sel_fwd & 0xFFFFu; row[1] = x.sel_fwd_hi; row[2] = x.sel_inv & 0xFFFFu; row[3] = x.sel_inv_hi;
+    row[4] = x.mul_l; row[5] = x.shift; row[6] = x.mask; row[7] = 0;
+  }
+  if (threadIdx.x < 128) {
+    const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
+    smem_raw[SM_LEGAL + threadIdx.x] =
+        (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u));
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
@@ -117,7 +209,6 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
   mbar_wait(bar, 0);
-  const uint32_t one = tabs->one;
 
   while (quad < nquads) {
     // prefetch this thread's next quad
@@ -147,17 +238,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       w = make_uint4(t[0], t[1], t[2], t[3]);
     }
 
-    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, f0, f1, c0, c1;
-    slide_board<true>(ba.x, ba.y, a4 & 3u, tabs, slut, glut, n0l, n0h, rw0, f0, c0, one);
-    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.x, p4, o4 & 0xFFu, f0, one);
-    slide_board<true>(ba.z, ba.w, (a4 >> 8) & 3u, tabs, slut, glut, n1l, n1h, rw1, f1, c1, one);
-    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.y, p4, (o4 >> 8) & 0xFFu, f1, one);
+    // the four action bytes -> four table-row offsets (action * 32) in one AND + shift
+    const uint32_t a32 = (a4 & 0x03030303u) << 5;
+    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3;
+    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4440), glut, ba.x, ba.y, w.x, p4,
+                               o4 & 0xFFu, n0l, n0h, rw0, f0);
+    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4441), glut, ba.z, ba.w, w.y, p4,
+                               (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1);
     st_stream_v4(next2 + 2 * quad, make_uint4(n0l, n0h, n1l, n1h));
-    uint32_t rw2, rw3, f2, f3;
-    slide_board<true>(bb.x, bb.y, (a4 >> 16) & 3u, tabs, slut, glut, n0l, n0h, rw2, f2, c0, one);
-    finish_board<HAS_OVERRIDE>(n0l, n0h, c0, w.z, p4, (o4 >> 16) & 0xFFu, f2, one);
-    slide_board<true>(bb.z, bb.w, (a4 >> 24) & 3u, tabs, slut, glut, n1l, n1h, rw3, f3, c1, one);
-    finish_board<HAS_OVERRIDE>(n1l, n1h, c1, w.w, p4, o4 >> 24, f3, one);
+    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4442), glut, bb.x, bb.y, w.z, p4,
+                               (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2);
+    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4443), glut, bb.z, bb.w, w.w, p4,
+                               o4 >> 24, n1l, n1h, rw3, f3);
     st_stream_v4(next2 + 2 * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
     flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
