@@ -56,10 +56,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
 template <bool HAS_OVERRIDE>
 __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
-                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags, uint32_t one = 1u) {
   const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w, e29);
+    spawn_kth_empty(nlo, nhi, w, e29, one);
   } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
@@ -77,8 +77,16 @@ constexpr int STREAM_THREADS = 1024;
 // pointers ptxas re-derived the shared window base (S2R + MOV + LEA) for every board.
 constexpr uint32_t SM_ACT = (uint32_t)LUT_SMEM_BYTES;   // 4 rows x 32 B: per-action transform constants
 constexpr uint32_t SM_LEGAL = SM_ACT + 128;             // 4 rows x 32 B: flags byte per (action, frame mask)
-constexpr uint32_t SM_BAR = SM_LEGAL + 128;             // mbarrier
+constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // runtime constants {4, 1, -, -}
+constexpr uint32_t SM_BAR = SM_CONST + 16;              // mbarrier
 constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
+
+// ptxas turns idx * 4 + base into LEA and x + c into VIADD/IADD3, all on the saturated ALU pipe.
+// Multiplying by a constant it cannot see (read from shared memory at run time) keeps the
+// operation an IMAD on the FMA pipe, which is ~25 % busy in this kernel.
+#ifndef B2048_FMA_ADDR
+#define B2048_FMA_ADDR 1
+#endif
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
@@ -102,7 +110,8 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 template <bool HAS_OVERRIDE>
 __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const uint32_t* __restrict__ glut,
                                              uint32_t lo, uint32_t hi, uint32_t w, uint32_t p4, uint32_t ovr,
-                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags) {
+                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags,
+                                             uint32_t four, uint32_t one) {
   const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
   const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
   uint32_t zl = __byte_perm(lo, hi, xa.x);
@@ -119,10 +128,17 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
     e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
     extra = extra_reward_eeee(zl, zh);
   } else {
+#if B2048_FMA_ADDR
+    e0 = lds32(__byte_perm(zl, 0u, 0x4410) * four + sbase);   // PRMT (ALU) + IMAD (FMA) per row
+    e1 = lds32(__byte_perm(zl, 0u, 0x4432) * four + sbase);
+    e2 = lds32(__byte_perm(zh, 0u, 0x4410) * four + sbase);
+    e3 = lds32(__byte_perm(zh, 0u, 0x4432) * four + sbase);
+#else
     e0 = lds32(sbase + ((zl * 4u) & 0x3FFFCu));
     e1 = lds32(sbase + __byte_perm(zl, 0u, 0x4432) * 4u);
     e2 = lds32(sbase + ((zh * 4u) & 0x3FFFCu));
     e3 = lds32(sbase + __byte_perm(zh, 0u, 0x4432) * 4u);
+#endif
   }
   uint32_t wl = (e0 & 0xFFFFu) + (e1 << 16);
   uint32_t wh = (e2 & 0xFFFFu) + (e3 << 16);
@@ -134,9 +150,9 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
 
   // legality of the input board in the transformed frame (see slide_board)
   const uint32_t changed = (wl ^ zl) | (wh ^ zh);
-  const uint32_t n_l = nz3(zl), n_h = nz3(zh);
+  const uint32_t n_l = nz3(zl, one), n_h = nz3(zh, one);
   const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = zh >> 16;
-  const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
+  const uint32_t ne_l = ne3_dirty(zl, v_l, one), ne_h = ne3_dirty(zh, v_h, one);
   const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = n_h >> 16;
   const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
@@ -152,7 +168,7 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
   }
   olo = __byte_perm(wl, wh, xa.z);
   ohi = __byte_perm(wl, wh, xa.w);
-  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags);
+  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags, one);
 }
 
 // ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
@@ -179,6 +195,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     uint32_t* row = reinterpret_cast<uint32_t*>(smem_raw + SM_ACT + 32 * threadIdx.x);
     row[0] = x.sel_fwd & 0xFFFFu; row[1] = x.sel_fwd_hi; row[2] = x.sel_inv & 0xFFFFu; row[3] = x.sel_inv_hi;
     row[4] = x.mul_l; row[5] = x.shift; row[6] = x.mask; row[7] = 0;
+  }
+  if (threadIdx.x == 0) {
+    uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
+    k[0] = 4u; k[1] = 1u; k[2] = 0u; k[3] = 0u;
   }
   if (threadIdx.x < 128) {
     const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
@@ -209,6 +229,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
   mbar_wait(bar, 0);
+  const uint32_t four = lds32(sbase + SM_CONST), one = lds32(sbase + SM_CONST + 4);
 
   while (quad < nquads) {
     // prefetch this thread's next quad
@@ -242,14 +263,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     const uint32_t a32 = (a4 & 0x03030303u) << 5;
     uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3;
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4440), glut, ba.x, ba.y, w.x, p4,
-                               o4 & 0xFFu, n0l, n0h, rw0, f0);
+                               o4 & 0xFFu, n0l, n0h, rw0, f0, four, one);
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4441), glut, ba.z, ba.w, w.y, p4,
-                               (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1);
+                               (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, four, one);
     st_stream_v4(next2 + 2 * quad, make_uint4(n0l, n0h, n1l, n1h));
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4442), glut, bb.x, bb.y, w.z, p4,
-                               (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2);
+                               (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, four, one);
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4443), glut, bb.z, bb.w, w.w, p4,
-                               o4 >> 24, n1l, n1h, rw3, f3);
+                               o4 >> 24, n1l, n1h, rw3, f3, four, one);
     st_stream_v4(next2 + 2 * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
     flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
