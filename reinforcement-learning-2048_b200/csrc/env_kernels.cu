@@ -70,7 +70,10 @@ __device__ __forceinline__ uint32_t pick_word(const uint4& r, uint32_t j) {
   return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
 }
 
-constexpr int STREAM_THREADS = 1024;
+#ifndef B2048_STREAM_THREADS
+#define B2048_STREAM_THREADS 1024
+#endif
+constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 
 // Shared-memory map of the streaming kernel (byte offsets from the start of dynamic smem).  All
 // table reads use explicit shared-space loads on a 32-bit base address computed once: with generic
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   }
   if (threadIdx.x == 0) {
     uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
-    k[0] = 4u; k[1] = 1u; k[2] = 0u; k[3] = 0u;
+    k[0] = 4u; k[1] = 1u; k[2] = 2u; k[3] = 0u;
   }
   if (threadIdx.x < 128) {
     const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
