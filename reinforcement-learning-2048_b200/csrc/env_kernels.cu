@@ -217,38 +217,41 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut) + off, CHUNK, bar);
   }
 
-  const int64_t stride = (int64_t)gridDim.x * STREAM_THREADS;
-  int64_t quad = (int64_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+  // 32-bit quad index (the host wrapper keeps nquads < 2^32): every global address is then one
+  // IMAD.WIDE (base + index * size) on the FMA pipe instead of 64-bit LEA pairs on the ALU pipe.
+  const uint32_t stride = gridDim.x * STREAM_THREADS;
+  const uint32_t nq = (uint32_t)nquads;
+  uint32_t quad = blockIdx.x * STREAM_THREADS + threadIdx.x;
   const uint32_t base_mis = (uint32_t)index_base & 3u;
+  const uint64_t pidx_base = index_base >> 2;
   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
 
   // first loads are issued before waiting for the table
   uint4 ba = make_uint4(0, 0, 0, 0), bb = ba;
   uint32_t a4 = 0, o4 = 0xFFFFFFFFu;
-  if (quad < nquads) {
-    ba = ld_stream_v4(boards2 + 2 * quad);
-    bb = ld_stream_v4(boards2 + 2 * quad + 1);
+  if (quad < nq) {
+    ba = ld_stream_v4(boards2 + 2u * quad);
+    bb = ld_stream_v4(boards2 + 2u * quad + 1);
     a4 = ld_stream_u32(actions4 + quad);
     if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
   mbar_wait(bar, 0);
   const uint32_t four = lds32(sbase + SM_CONST), one = lds32(sbase + SM_CONST + 4);
 
-  while (quad < nquads) {
-    // prefetch this thread's next quad
-    const int64_t nxt = quad + stride;
+  while (quad < nq) {
+    // prefetch this thread's next quad (stride < 2^18, so the sum cannot wrap for nq < 2^32 - 2^18)
+    const uint32_t nxt = quad + stride;
     uint4 na = make_uint4(0, 0, 0, 0), nb = na;
     uint32_t an = 0, on = 0xFFFFFFFFu;
-    if (nxt < nquads) {
-      na = ld_stream_v4(boards2 + 2 * nxt);
-      nb = ld_stream_v4(boards2 + 2 * nxt + 1);
+    if (nxt < nq) {
+      na = ld_stream_v4(boards2 + 2u * nxt);
+      nb = ld_stream_v4(boards2 + 2u * nxt + 1);
       an = ld_stream_u32(actions4 + nxt);
       if (HAS_OVERRIDE) on = ld_stream_u32(override4 + nxt);
     }
 
     // one Philox4x32-10 call per aligned group of four global board indices
-    const uint64_t g0 = index_base + 4ull * (uint64_t)quad;
-    const uint64_t pidx = g0 >> 2;
+    const uint64_t pidx = pidx_base + quad;
     uint4 w = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
     if (base_mis != 0) {  // uniform: index_base not a multiple of 4 -> the quad straddles two calls
       const uint64_t p1 = pidx + 1;
@@ -269,12 +272,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                                o4 & 0xFFu, n0l, n0h, rw0, f0, four, one);
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4441), glut, ba.z, ba.w, w.y, p4,
                                (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, four, one);
-    st_stream_v4(next2 + 2 * quad, make_uint4(n0l, n0h, n1l, n1h));
+    st_stream_v4(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h));
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4442), glut, bb.x, bb.y, w.z, p4,
                                (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, four, one);
     stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4443), glut, bb.z, bb.w, w.w, p4,
                                o4 >> 24, n1l, n1h, rw3, f3, four, one);
-    st_stream_v4(next2 + 2 * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
+    st_stream_v4(next2 + 2u * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
     flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
 
@@ -539,15 +542,21 @@ cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint
                          reinterpret_cast<uintptr_t>(ovr)) & 3u) == 0;
   int64_t done = 0;
   if (aligned && n >= STREAM_MIN_BOARDS) {
-    const int64_t nquads = n / 4;
-    step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
-        reinterpret_cast<const uint4*>(boards), reinterpret_cast<const uint32_t*>(actions),
-        reinterpret_cast<uint4*>(next), reinterpret_cast<uint4*>(reward),
-        reinterpret_cast<uint32_t*>(flags), nquads, ctx->lut, philox_keys(seed, DOM_SPAWN), step,
-        index_base, p4, reinterpret_cast<const uint32_t*>(ovr));
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    done = nquads * 4;
+    // the kernel indexes quads with 32 bits: launch in pieces of at most 2^33 boards (never in practice)
+    constexpr int64_t MAX_QUADS = (int64_t)1 << 31;
+    const int64_t nquads_total = n / 4;
+    for (int64_t q0 = 0; q0 < nquads_total; q0 += MAX_QUADS) {
+      const int64_t nquads = (nquads_total - q0 < MAX_QUADS) ? (nquads_total - q0) : MAX_QUADS;
+      const int64_t b0 = q0 * 4;
+      step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
+          reinterpret_cast<const uint4*>(boards + b0), reinterpret_cast<const uint32_t*>(actions + b0),
+          reinterpret_cast<uint4*>(next + b0), reinterpret_cast<uint4*>(reward + b0),
+          reinterpret_cast<uint32_t*>(flags + b0), nquads, ctx->lut, philox_keys(seed, DOM_SPAWN), step,
+          index_base + (uint64_t)b0, p4, ovr ? reinterpret_cast<const uint32_t*>(ovr + b0) : nullptr);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+    done = nquads_total * 4;
   }
   if (done < n) {
     const int64_t m = n - done;
