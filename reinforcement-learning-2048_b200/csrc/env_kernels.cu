@@ -143,8 +143,8 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
     e3 = lds32(sbase + __byte_perm(zh, 0u, 0x4432) * 4u);
 #endif
   }
-  uint32_t wl = (e0 & 0xFFFFu) + (e1 << 16);
-  uint32_t wh = (e2 & 0xFFFFu) + (e3 << 16);
+  uint32_t wl = __byte_perm(e0, e1, 0x5410);
+  uint32_t wh = __byte_perm(e2, e3, 0x5410);
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
   const uint32_t fl = h01 | h23;
@@ -159,9 +159,13 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
   const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = n_h >> 16;
   const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
-  const uint32_t m = (changed ? 1u : 0u) + ((fl & 0x40004000u) ? 2u : 0u) + (up ? 4u : 0u) +
-                     ((dn_l | (dn_h & 0x0000FFFFu)) ? 8u : 0u);
-  flags = lds8(sa + m + SM_LEGAL);             // legal | DONE | CHANGED
+  // table index built on top of the row address with four predicated adds (no SEL, no final add)
+  uint32_t fa = sa;
+  if (changed) fa += 1u;
+  if (fl & 0x40004000u) fa += 2u;
+  if (up) fa += 4u;
+  if (dn_l | (dn_h & 0x0000FFFFu)) fa += 8u;
+  flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED
   if (fl & 0x80008000u) flags |= B2048_FLAG_OVERFLOW;
 
   {
@@ -268,14 +272,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     // the four action bytes -> four table-row offsets (action * 32) in one AND + shift
     const uint32_t a32 = (a4 & 0x03030303u) << 5;
     uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3;
-    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4440), glut, ba.x, ba.y, w.x, p4,
+    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4440) * one + sbase, glut, ba.x, ba.y, w.x, p4,
                                o4 & 0xFFu, n0l, n0h, rw0, f0, four, one);
-    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4441), glut, ba.z, ba.w, w.y, p4,
+    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4441) * one + sbase, glut, ba.z, ba.w, w.y, p4,
                                (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, four, one);
     st_stream_v4(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h));
-    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4442), glut, bb.x, bb.y, w.z, p4,
+    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4442) * one + sbase, glut, bb.x, bb.y, w.z, p4,
                                (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, four, one);
-    stream_board<HAS_OVERRIDE>(sbase, sbase + __byte_perm(a32, 0u, 0x4443), glut, bb.z, bb.w, w.w, p4,
+    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4443) * one + sbase, glut, bb.z, bb.w, w.w, p4,
                                o4 >> 24, n1l, n1h, rw3, f3, four, one);
     st_stream_v4(next2 + 2u * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
