@@ -30,6 +30,9 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
           [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    extra = os.environ.get("B2048_NVCC_EXTRA")        # kernel-variant experiments only
+    if extra:
+        cmd += extra.split()
     subprocess.check_call(cmd, cwd=CSRC)
     return OUT
 

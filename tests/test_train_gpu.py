@@ -151,3 +151,47 @@ def test_fast_conv_forward_equals_cudnn_path(cuda):
     fast(x).square().sum().backward()
     for u, p in zip(g1, net.parameters()):
         np.testing.assert_allclose(p.grad.cpu().numpy(), u.cpu().numpy(), rtol=1e-10, atol=1e-10 * float(u.abs().max()))
+
+
+def test_batched_player_baselines(cuda):
+    """The reference's player.py policies at scale: random-legal and up-left baselines."""
+    from b2048.player import BatchedPlayer
+    rnd = BatchedPlayer(4096, device=cuda, seed=1).random_baseline(6000)
+    # random legal play: ~110-160 moves, max tile mostly 64/128/256 (reference notebook, BASELINE.md)
+    assert rnd["games"] == 8192 and 65 < rnd["mean_moves"] < 130, rnd        # 2 complete games per board; reference: ~92 (BASELINE.md, 20 games)
+    assert max(rnd["max_tile_hist"], key=rnd["max_tile_hist"].get) in (64, 128, 256)
+    ul = BatchedPlayer(4096, device=cuda, seed=2).upleft_baseline(6000)
+    assert ul["games"] == 8192 and 50 < ul["mean_moves"] < 400, ul
+    assert ul["mean_merge_score"] > 300
+
+
+def test_checkpoint_resume_is_bit_identical(cuda, tmp_path):
+    """Save mid-run, keep going, reload, redo: same boards, same replay contents, same weights."""
+    from b2048 import checkpoint
+    torch.manual_seed(4)
+
+    def make():
+        ve = VectorEnv(2048, device=cuda, seed=21)
+        ring = b2048.ReplayRing(15000, device=cuda)
+        up = DDQNUpdater(dense_model().to(cuda), ring, batch_size=512, lr=1e-3, conv=False, use_graph=False, seed=3)
+        return ve, ring, up
+
+    def run(ve, ring, up, steps):
+        for _ in range(steps):
+            ve.step(replay=ring)
+            up.update()
+
+    torch.manual_seed(4)
+    ve, ring, up = make()
+    run(ve, ring, up, 6)
+    path = str(tmp_path / "ck.pt")
+    checkpoint.save(path, updater=up, vector_env=ve, extra={"note": "mid-run"})
+    run(ve, ring, up, 5)
+    want = (ve.boards.clone(), ring.s.clone(), ring.head_size.clone(), [p.detach().clone() for p in up.model.parameters()])
+    torch.manual_seed(99)                         # different init: everything must come from the file
+    ve2, ring2, up2 = make()
+    assert checkpoint.load(path, updater=up2, vector_env=ve2)["note"] == "mid-run"
+    run(ve2, ring2, up2, 5)
+    assert torch.equal(ve2.boards, want[0]) and torch.equal(ring2.s, want[1]) and torch.equal(ring2.head_size, want[2])
+    for p, q in zip(up2.model.parameters(), want[3]):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.cpu().numpy(), rtol=1e-12, atol=1e-14)
