@@ -109,47 +109,20 @@ __host__ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t doma
 
 // ---- nibble SWAR ------------------------------------------------------------------------------
 // The step kernel is bound by the SM's integer ALU pipe (LOP3/SHF/PRMT/ISETP/SEL: one warp
-// instruction per 2 cycles per sub-partition, measured in profiles/ubench), not by HBM.  Where an
-// operation has an equivalent on the FMA pipe it is written that way on purpose:
-//   x >> k  ->  __umulhi(x, 1 << (32-k))   (IMAD.HI)      x << k -> x * (1 << k)  (IMAD.SHL)
-//   a | b with disjoint bits -> a + b / a * m + b          (IMAD)
-#ifndef B2048_SHR_FMA
-#define B2048_SHR_FMA 0
-#endif
-__device__ __forceinline__ uint32_t shr_fma(uint32_t v, int k) {
-#if B2048_SHR_FMA
-  return __umulhi(v, 1u << (32 - k));   // IMAD.HI: 4 cycles on the FMA pipe
-#else
-  return v >> k;                        // SHF: 2 cycles on the ALU pipe
-#endif
-}
-
-// t + 0x77777777 (the carry-free nibble add of the non-zero tests).  `one` is a runtime 1 (read from
-// shared memory, so ptxas cannot fold it): t * one + c is issued as IMAD on the FMA pipe instead of
-// an integer add on the ALU pipe.  Measured on B200: no gain (0.4335 vs 0.4294 ms per 64Mi boards;
-// ptxas already balances plain adds across both pipes), so the default is the plain add.
-#ifndef B2048_ADD_FMA
-#define B2048_ADD_FMA 0
-#endif
-__device__ __forceinline__ uint32_t add7(uint32_t t, uint32_t one) {
-#if B2048_ADD_FMA
-  return t * one + 0x77777777u;
-#else
-  (void)one;
-  return t + 0x77777777u;
-#endif
-}
-
+// instruction per 2 cycles per sub-partition, measured in profiles/ubench), not by HBM, so the code
+// below is written to minimise ALU-pipe instructions.  Measured on B200 and NOT adopted: right
+// shifts as IMAD.HI (4-cycle issue on the FMA pipe), the +0x7777.. adds as IMAD (no gain: ptxas
+// already balances plain adds across both pipes), booleans as IMAD.WIDE carries.
 // bit 3 of every nibble set iff the nibble is non-zero (carry-free: 7+7 < 16).
-__device__ __forceinline__ uint32_t nz3(uint32_t v, uint32_t one = 1u) {
-  return (add7(v & 0x77777777u, one) | v) & 0x88888888u;
+__device__ __forceinline__ uint32_t nz3(uint32_t v) {
+  return (((v & 0x77777777u) + 0x77777777u) | v) & 0x88888888u;
 }
 // same for a ^ b, WITHOUT the final mask (bits other than bit 3 of each nibble are garbage).
 // Two 3-input LOP3s, written as lop3 so that ptxas does not split the xor out (one ALU op more).
-__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b, uint32_t one = 1u) {
+__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b) {
   uint32_t t, r;
   asm("lop3.b32 %0, %1, %2, 0x77777777, 0x28;" : "=r"(t) : "r"(a), "r"(b));   // (a ^ b) & 0x7777...
-  t = add7(t, one);
+  t += 0x77777777u;
   asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(r) : "r"(t), "r"(a), "r"(b));   // t | (a ^ b)
   return r;
 }
@@ -183,31 +156,26 @@ __device__ __forceinline__ uint32_t legal_mask(uint32_t lo, uint32_t hi) {
 // is the nibble part of the 4x4 transpose (s = 12, m = 0x0000F0F0) or the nibble swap inside each
 // byte of a horizontal flip (s = 4, m = 0x0F0F0F0F); for `left` m = 0.  Both halves are
 // involutions, so the inverse is delta-swap first, then the inverse byte permutation.
-// The shifts are stored as multipliers (mul_l = 2^s, mul_r = 2^(32-s)) so that they run on the
-// FMA pipe (IMAD / IMAD.HI) instead of the ALU pipe.
+// The left shift is stored as a multiplier (mul_l = 2^s) so that it issues as IMAD on the FMA pipe.
 struct ActXform {
   uint32_t sel_fwd;  // lo selector | hi selector << 16
   uint32_t sel_inv;
   uint32_t mul_l;    // 1 << s
-  uint32_t mul_r;    // 1 << (32 - s)
+  uint32_t unused;   // keeps the row 32 bytes
   uint32_t mask;
   uint32_t shift;    // s
   uint32_t sel_fwd_hi, sel_inv_hi;
 };
 
 __host__ __device__ constexpr ActXform act_xform(int a) {
-  return a == 0   ? ActXform{0x6240u | (0x7351u << 16), 0x6240u | (0x7351u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 12u, 0x7351u, 0x7351u}
-         : a == 1 ? ActXform{0x0426u | (0x1537u << 16), 0x5173u | (0x4062u << 16), 1u << 12, 1u << 20, 0x0000F0F0u, 12u, 0x1537u, 0x4062u}
-         : a == 2 ? ActXform{0x3210u | (0x7654u << 16), 0x3210u | (0x7654u << 16), 1u << 4, 1u << 28, 0u, 4u, 0x7654u, 0x7654u}
-                  : ActXform{0x2301u | (0x6745u << 16), 0x2301u | (0x6745u << 16), 1u << 4, 1u << 28, 0x0F0F0F0Fu, 4u, 0x6745u, 0x6745u};
+  return a == 0   ? ActXform{0x6240u | (0x7351u << 16), 0x6240u | (0x7351u << 16), 1u << 12, 0u, 0x0000F0F0u, 12u, 0x7351u, 0x7351u}
+         : a == 1 ? ActXform{0x0426u | (0x1537u << 16), 0x5173u | (0x4062u << 16), 1u << 12, 0u, 0x0000F0F0u, 12u, 0x1537u, 0x4062u}
+         : a == 2 ? ActXform{0x3210u | (0x7654u << 16), 0x3210u | (0x7654u << 16), 1u << 4, 0u, 0u, 4u, 0x7654u, 0x7654u}
+                  : ActXform{0x2301u | (0x6745u << 16), 0x2301u | (0x6745u << 16), 1u << 4, 0u, 0x0F0F0F0Fu, 4u, 0x6745u, 0x6745u};
 }
 
 __device__ __forceinline__ uint32_t delta_swap(uint32_t v, const ActXform& x) {
-#if B2048_SHR_FMA
-  const uint32_t t = (v ^ __umulhi(v, x.mul_r)) & x.mask;
-#else
   const uint32_t t = (v ^ (v >> x.shift)) & x.mask;
-#endif
   return v ^ t ^ (t * x.mul_l);
 }
 
@@ -228,13 +196,10 @@ __host__ __device__ constexpr uint32_t zframe_to_legal(int a, uint32_t m) {
 struct SmemTabs {
   ActXform act[4];        // 128 B
   uint8_t legal[4][16];   //  64 B
-  uint32_t one;           // runtime 1 for add7()
-  uint32_t pad[3];
 };
 
 __device__ __forceinline__ void fill_tabs(SmemTabs* t) {
   if (threadIdx.x < 4) t->act[threadIdx.x] = act_xform((int)threadIdx.x);
-  if (threadIdx.x == 0) t->one = 1u;
   if (threadIdx.x < 64) t->legal[threadIdx.x >> 4][threadIdx.x & 15] =
       (uint8_t)zframe_to_legal((int)(threadIdx.x >> 4), threadIdx.x & 15u);
 }
@@ -301,7 +266,7 @@ template <bool SMEM, bool LEGAL = true>
 __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a, const SmemTabs* tabs,
                                             const uint32_t* slut, const uint32_t* __restrict__ glut,
                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward,
-                                            uint32_t& flags, uint32_t& changed, uint32_t one = 1u) {
+                                            uint32_t& flags, uint32_t& changed) {
   const ActXform x = tabs->act[a];
   uint32_t zl = __byte_perm(lo, hi, x.sel_fwd);
   uint32_t zh = __byte_perm(lo, hi, x.sel_fwd_hi);
@@ -322,10 +287,10 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
   // perpendicular axis by SWAR on z: pair (row r, row r+1) sits at row r.
   changed = (wl ^ zl) | (wh ^ zh);
   if (LEGAL) {
-    const uint32_t n_l = nz3(zl, one), n_h = nz3(zh, one);
-    const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = shr_fma(zh, 16);
-    const uint32_t ne_l = ne3_dirty(zl, v_l, one), ne_h = ne3_dirty(zh, v_h, one);
-    const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = shr_fma(n_h, 16);
+    const uint32_t n_l = nz3(zl), n_h = nz3(zh);
+    const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = (zh >> 16);
+    const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
+    const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = (n_h >> 16);
     const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
     const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
     const uint32_t m = (changed ? 1u : 0u) | ((fl & 0x40004000u) ? 2u : 0u) | (up ? 4u : 0u) |
@@ -346,19 +311,19 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
 // Put exponent e (0 = nothing) into the k-th empty cell (row-major) where
 // k = floor(w_pos * n_empty / 2^32).  Requires at most 15 empty cells.  `e29` = e << 29.
 __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint32_t w_pos,
-                                                uint32_t e29, uint32_t one = 1u) {
-  const uint32_t e3_lo = ~(add7(lo & 0x77777777u, one) | lo) & 0x88888888u;  // bit 3 of empty nibbles
-  const uint32_t e3_hi = ~(add7(hi & 0x77777777u, one) | hi) & 0x88888888u;
-  const uint32_t e_lo = shr_fma(e3_lo, 3), e_hi = shr_fma(e3_hi, 3);
+                                                uint32_t e29) {
+  const uint32_t e3_lo = ~(((lo & 0x77777777u) + 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
+  const uint32_t e3_hi = ~(((hi & 0x77777777u) + 0x77777777u) | hi) & 0x88888888u;
+  const uint32_t e_lo = (e3_lo >> 3), e_hi = (e3_hi >> 3);
   // inclusive prefix counts per nibble: multiply by 0x11111111 (counts <= 15 never carry)
   const uint32_t p_lo = e_lo * 0x11111111u;
-  const uint32_t c_lo = shr_fma(p_lo, 28);
+  const uint32_t c_lo = (p_lo >> 28);
   const uint32_t p_hi = e_hi * 0x11111111u + c_lo * 0x11111111u;
-  const uint32_t cnt = shr_fma(p_hi, 28);
+  const uint32_t cnt = (p_hi >> 28);
   const uint32_t tgt = __umulhi(w_pos, cnt) * 0x11111111u + 0x11111111u;  // (k+1) in every nibble
   // the chosen nibble is the empty one whose prefix count equals k+1
-  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt, one) & e3_lo;
-  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt, one) & e3_hi;
+  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt) & e3_lo;
+  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt) & e3_hi;
   // exactly one bit (bit 3 of the chosen nibble) is set across h_lo/h_hi; the cell is empty so + == |
   // hi32(h * (e << 29)) = (h >> 3) * e: shift, scale and insert in one IMAD.HI each
   lo = __umulhi(h_lo, e29) + lo;

@@ -56,10 +56,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
 template <bool HAS_OVERRIDE>
 __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
-                                             uint32_t p4, uint32_t ovr, uint32_t& flags, uint32_t one = 1u) {
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
   const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w, e29, one);
+    spawn_kth_empty(nlo, nhi, w, e29);
   } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
@@ -84,9 +84,9 @@ constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // runtime constants {4,
 constexpr uint32_t SM_BAR = SM_CONST + 16;              // mbarrier
 constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
 
-// ptxas turns idx * 4 + base into LEA and x + c into VIADD/IADD3, all on the saturated ALU pipe.
-// Multiplying by a constant it cannot see (read from shared memory at run time) keeps the
-// operation an IMAD on the FMA pipe, which is ~25 % busy in this kernel.
+// ptxas turns idx * 4 + base into LEA on the saturated ALU pipe.  Multiplying by a constant it
+// cannot see (4 and 1 read from shared memory at run time) keeps the table addresses IMADs on the
+// FMA pipe, which is ~28 % busy in this kernel (measured: 0.397 -> 0.3895 ms per 64Mi boards).
 #ifndef B2048_FMA_ADDR
 #define B2048_FMA_ADDR 1
 #endif
@@ -153,9 +153,9 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
 
   // legality of the input board in the transformed frame (see slide_board)
   const uint32_t changed = (wl ^ zl) | (wh ^ zh);
-  const uint32_t n_l = nz3(zl, one), n_h = nz3(zh, one);
+  const uint32_t n_l = nz3(zl), n_h = nz3(zh);
   const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = zh >> 16;
-  const uint32_t ne_l = ne3_dirty(zl, v_l, one), ne_h = ne3_dirty(zh, v_h, one);
+  const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
   const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = n_h >> 16;
   const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
@@ -175,7 +175,7 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
   }
   olo = __byte_perm(wl, wh, xa.z);
   ohi = __byte_perm(wl, wh, xa.w);
-  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags, one);
+  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags);
 }
 
 // ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
