@@ -208,6 +208,15 @@ int ddqn_target_loss(const double* q_next_online, const double* q_next_target, c
                      float gamma_f32, int use_double, double* target, double* q_sa, double* loss,
                      double* grad_q_cur, int64_t B, void* stream);
 
+/* Fused Adam step on one flat float64 parameter buffer (= optimizer.step() of torch.optim.Adam
+ * without weight decay / amsgrad, configs/double_dqn_*.py: Adam(lr=1e-2); src/dqn_lib.py:163).
+ *   t = step_counter[0] + 1;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g
+ *   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps);  step_counter[0] = t
+ * `step_counter` is a device int64 so that a captured CUDA graph advances it on every replay. */
+int ddqn_adam_step(double* params, const double* grads, double* exp_avg, double* exp_avg_sq,
+                   int64_t* step_counter, int64_t n, double lr, double beta1, double beta2,
+                   double eps, void* stream);
+
 /* ---- K0: batched epsilon-greedy ---------------------------------------------------------------- */
 
 /* = epsilon_greedy_policy, src/dqn_lib.py:16-30, for n boards.  With probability eps the action is

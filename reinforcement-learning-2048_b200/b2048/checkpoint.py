@@ -47,7 +47,9 @@ def load(path: str, updater=None, vector_env=None, ring=None) -> dict:
     if ck.get("format") != "b2048-checkpoint-1":
         raise ValueError("not a b2048 checkpoint")
     if updater is not None:
-        updater.model.load_state_dict(ck["model"])
+        with torch.no_grad():                     # in place: the parameters are views of one flat buffer
+            for k, v in updater.model.state_dict().items():
+                v.copy_(ck["model"][k])
         updater.target.load_state_dict(ck["target"])
         updater.opt.load_state_dict(ck["optimizer"])
         updater.updates = ck["updates"]

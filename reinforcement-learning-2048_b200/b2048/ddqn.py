@@ -86,3 +86,32 @@ def egreedy_select(q, flags, epsilon, seed=2052, ctr=0, index_base=0, override=N
                                              index_base & _U64, _ptr(override), _ptr(actions), _ptr(max_q), n,
                                              _stream(flags)), "egreedy_select")
     return actions, max_q
+
+
+class FusedAdam:
+    """torch.optim.Adam (no weight decay, no amsgrad) as ONE kernel over flat float64 buffers
+    (`ddqn_adam_step`); the step counter lives on the device, so the update is graph-capturable.
+    The stock capturable Adam launches ~35 kernels per step for the conv Q-network."""
+
+    def __init__(self, flat_params: torch.Tensor, flat_grads: torch.Tensor, lr=1e-2, betas=(0.9, 0.999), eps=1e-8):
+        assert flat_params.dtype == torch.float64 and flat_params.is_contiguous() and flat_grads.is_contiguous()
+        self.p, self.g = flat_params, flat_grads
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = torch.zeros_like(flat_params)
+        self.exp_avg_sq = torch.zeros_like(flat_params)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=flat_params.device)
+
+    def step(self) -> None:
+        dev = _dev(self.p)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddqn_adam_step(_ptr(self.p), _ptr(self.g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                                 _ptr(self.step_count), self.p.numel(), self.lr, self.betas[0],
+                                                 self.betas[1], self.eps, _stream(self.p)), "ddqn_adam_step")
+
+    def state_dict(self) -> dict:
+        return {"exp_avg": self.exp_avg.cpu(), "exp_avg_sq": self.exp_avg_sq.cpu(), "step": self.step_count.cpu(),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, st: dict) -> None:
+        self.exp_avg.copy_(st["exp_avg"]); self.exp_avg_sq.copy_(st["exp_avg_sq"]); self.step_count.copy_(st["step"])
+        self.lr, self.betas, self.eps = st["lr"], tuple(st["betas"]), st["eps"]

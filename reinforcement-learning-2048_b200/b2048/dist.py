@@ -68,6 +68,20 @@ class FlatGrads:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
 
+class FlatParams:
+    """One contiguous parameter buffer for a module; every parameter's .data is a view into it, so
+    a single fused optimizer kernel updates the whole network (the module keeps working as is)."""
+
+    def __init__(self, module: torch.nn.Module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.params = params
+        self.flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        off = 0
+        for p in params:
+            p.data = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+
 def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
     """Make every rank start from rank `src`'s weights (and buffers)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -19,7 +19,8 @@ def _conv_as_gemm(x: torch.Tensor, conv: nn.Conv2d) -> torch.Tensor:
     n, c, h, w = x.shape
     kh, kw = conv.kernel_size
     oh, ow = h - kh + 1, w - kw + 1
-    # patches [n, c, oh, ow, kh, kw] -> [n*oh*ow, c*kh*kw]; same (c, kh, kw) order as conv.weight
+    # patches [n, c, oh, ow, kh, kw] -> [n*oh*ow, c*kh*kw]; same (c, kh, kw) order as conv.weight.
+    # (F.unfold / im2col is ~100x slower in float64 on this stack: 120 ms per update, measured.)
     p = x.unfold(2, kh, 1).unfold(3, kw, 1).permute(0, 2, 3, 1, 4, 5).reshape(n * oh * ow, c * kh * kw)
     y = torch.addmm(conv.bias, p, conv.weight.reshape(conv.out_channels, -1).t())
     return y.reshape(n, oh, ow, conv.out_channels).permute(0, 3, 1, 2)

@@ -30,8 +30,10 @@ class DDQNUpdater:
         self.f_model, self.f_target = accelerate(self.model), accelerate(self.target)
         bdist.broadcast_module(self.model)
         bdist.broadcast_module(self.target)
-        self.grads = bdist.FlatGrads(model)
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, capturable=self.device.type == "cuda")
+        self.params = bdist.FlatParams(model)        # parameters and gradients as two flat buffers:
+        self.grads = bdist.FlatGrads(model)          #   one allreduce, one fused Adam kernel
+        self.opt = ddqn.FusedAdam(self.params.flat, self.grads.flat, lr=lr)
+        self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         kw = dict(device=self.device)
         B = self.B
         self.batch = (torch.empty((B, 16), dtype=torch.float64, **kw), torch.empty(B, dtype=torch.int64, **kw),
@@ -48,10 +50,19 @@ class DDQNUpdater:
     def _update_eager(self):
         states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
                                                                         out=self.batch)
-        with torch.no_grad():
+        # the two no-grad forwards run on a side stream next to the autograd forward (the kernels
+        # are small; the fork/join is captured into the CUDA graph)
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side), torch.no_grad():
             q_next_target = self.f_target(self._shape(next_states))
             q_next_online = self.f_model(self._shape(next_states)) if self.use_double else None
         q_cur = self.f_model(self._shape(states))
+        main.wait_stream(self.side)
+        if not torch.cuda.is_current_stream_capturing():      # eager mode: tell the allocator about the hand-over
+            q_next_target.record_stream(main)
+            if q_next_online is not None:
+                q_next_online.record_stream(main)
         loss, _, _ = ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones, self.gamma,
                                     self.use_double)
         self.grads.zero_()
@@ -75,7 +86,7 @@ class DDQNUpdater:
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            for _ in range(3):           # warm-up on a side stream (allocator, cuDNN/cuBLAS plans, Adam state)
+            for _ in range(3):           # warm-up on a side stream (allocator, cuBLAS plans)
                 self._update_eager()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)

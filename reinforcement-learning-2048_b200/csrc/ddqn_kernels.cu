@@ -91,6 +91,31 @@ __global__ void __launch_bounds__(K3_THREADS)
   }
 }
 
+__global__ void adam_kernel(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,
+                            double* __restrict__ v, const int64_t* __restrict__ step, int64_t n, double lr,
+                            double b1, double b2, double eps) {
+  __shared__ double s_step_size, s_inv_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = (double)(step[0] + 1);
+    s_step_size = lr / (1.0 - pow(b1, t));
+    s_inv_bc2_sqrt = 1.0 / sqrt(1.0 - pow(b2, t));
+  }
+  __syncthreads();
+  const double step_size = s_step_size, inv_bc2_sqrt = s_inv_bc2_sqrt;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double gi = g[i];
+    const double mi = b1 * m[i] + (1.0 - b1) * gi;
+    const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrt(vi) * inv_bc2_sqrt + eps);
+  }
+}
+
+__global__ void adam_bump_kernel(int64_t* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) step[0] += 1;
+}
+
 __global__ void egreedy_kernel(const double* __restrict__ q, const uint8_t* __restrict__ flags,
                                double eps, uint64_t seed, uint64_t ctr, uint64_t index_base,
                                const uint8_t* __restrict__ override_bytes,
@@ -156,6 +181,23 @@ extern "C" int ddqn_target_loss(const double* q_next_online, const double* q_nex
   ddqn_target_loss_kernel<<<(unsigned)blocks, K3_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       q_next_online, q_next_target, q_cur, actions, rewards, dones, gamma_f32, use_double, target,
       q_sa, loss, grad_q_cur, B, ctx->partials, ctx->ticket);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ddqn_adam_step(double* params, const double* grads, double* exp_avg, double* exp_avg_sq,
+                              int64_t* step_counter, int64_t n, double lr, double beta1, double beta2,
+                              double eps, void* stream) {
+  if (n <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !step_counter) return B2048_EINVAL;
+  int err = 0;
+  if (!current_ctx(&err)) return err;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;   // 8 CTAs of 256 threads per SM
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, step_counter, n, lr, beta1,
+                                                beta2, eps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  adam_bump_kernel<<<1, 32, 0, st>>>(step_counter);
   return (int)cudaGetLastError();
 }
 

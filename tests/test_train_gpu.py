@@ -114,7 +114,7 @@ def test_updater_graph_equals_eager_and_learns(cuda):
     # graph capture runs 3 warm-up + 1 capture update: restore weights, optimizer state and counter
     b.update()
     b.model.load_state_dict(base.state_dict())
-    b.opt = torch.optim.Adam(b.model.parameters(), lr=1e-3, capturable=True)
+    b.opt.exp_avg.zero_(); b.opt.exp_avg_sq.zero_(); b.opt.step_count.zero_()
     b.graph = None
     b.use_graph = False
     ring.head_size[2] = 0
