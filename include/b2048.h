@@ -208,6 +208,16 @@ int ddqn_target_loss(const double* q_next_online, const double* q_next_target, c
                      float gamma_f32, int use_double, double* target, double* q_sa, double* loss,
                      double* grad_q_cur, int64_t B, void* stream);
 
+/* Patch gather / scatter for the conv Q-network's tiny convolutions written as GEMMs
+ * (configs/double_dqn_conv.py:19-28: kernel_size 2, stride 1, no padding).
+ *   conv_patches_f64:      x [n,c,h,w] -> cols [n*oh*ow, c*kh*kw], (c,kh,kw) order like conv.weight
+ *   conv_patches_grad_f64: d cols -> d x (each input element sums the <= kh*kw patches that read
+ *                          it: a gather, deterministic, no atomics) */
+int conv_patches_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
+                     void* stream);
+int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
+                          int kw, void* stream);
+
 /* Fused Adam step on one flat float64 parameter buffer (= optimizer.step() of torch.optim.Adam
  * without weight decay / amsgrad, configs/double_dqn_*.py: Adam(lr=1e-2); src/dqn_lib.py:163).
  *   t = step_counter[0] + 1;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g

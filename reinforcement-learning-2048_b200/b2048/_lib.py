@@ -52,6 +52,8 @@ SIGNATURES = {
     "ddqn_target_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p]),
+    "conv_patches_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "conv_patches_grad_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ddqn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double,
                                ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
     "egreedy_select": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_uint64, c_uint64, c_uint64,

@@ -15,13 +15,47 @@ import torch.nn.functional as F
 from torch import nn
 
 
+class _Patches(torch.autograd.Function):
+    """x [n,c,h,w] -> cols [n*oh*ow, c*kh*kw] with one gather kernel each way (conv_patches_f64 /
+    conv_patches_grad_f64).  torch's x.unfold(...).unfold(...) backward costs two scatter kernels
+    plus fills (~90 us per update for the second conv), F.unfold is ~100x slower in float64."""
+
+    @staticmethod
+    def forward(ctx, x, kh, kw):
+        from . import _lib
+        from .env import _ptr, _stream
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        ctx.shape, ctx.k = (n, c, h, w), (kh, kw)
+        cols = torch.empty((n * (h - kh + 1) * (w - kw + 1), c * kh * kw), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().conv_patches_f64(_ptr(x), _ptr(cols), n, c, h, w, kh, kw, _stream(x)),
+                       "conv_patches_f64")
+        return cols
+
+    @staticmethod
+    def backward(ctx, dcols):
+        from . import _lib
+        from .env import _ptr, _stream
+        n, c, h, w = ctx.shape
+        kh, kw = ctx.k
+        dcols = dcols.contiguous()
+        dx = torch.empty((n, c, h, w), dtype=dcols.dtype, device=dcols.device)
+        with torch.cuda.device(dcols.device):
+            _lib.check(_lib.lib().conv_patches_grad_f64(_ptr(dcols), _ptr(dx), n, c, h, w, kh, kw, _stream(dcols)),
+                       "conv_patches_grad_f64")
+        return dx, None, None
+
+
 def _conv_as_gemm(x: torch.Tensor, conv: nn.Conv2d) -> torch.Tensor:
     n, c, h, w = x.shape
     kh, kw = conv.kernel_size
     oh, ow = h - kh + 1, w - kw + 1
-    # patches [n, c, oh, ow, kh, kw] -> [n*oh*ow, c*kh*kw]; same (c, kh, kw) order as conv.weight.
-    # (F.unfold / im2col is ~100x slower in float64 on this stack: 120 ms per update, measured.)
-    p = x.unfold(2, kh, 1).unfold(3, kw, 1).permute(0, 2, 3, 1, 4, 5).reshape(n * oh * ow, c * kh * kw)
+    # patches [n*oh*ow, c*kh*kw] in the (c, kh, kw) order of conv.weight
+    if x.is_cuda and x.dtype == torch.float64:
+        p = _Patches.apply(x, kh, kw)
+    else:
+        p = x.unfold(2, kh, 1).unfold(3, kw, 1).permute(0, 2, 3, 1, 4, 5).reshape(n * oh * ow, c * kh * kw)
     y = torch.addmm(conv.bias, p, conv.weight.reshape(conv.out_channels, -1).t())
     return y.reshape(n, oh, ow, conv.out_channels).permute(0, 3, 1, 2)
 
