@@ -227,6 +227,30 @@ int ddqn_adam_step(double* params, const double* grads, double* exp_avg, double*
                    int64_t* step_counter, int64_t n, double lr, double beta1, double beta2,
                    double eps, void* stream);
 
+/* Gradient allreduce fused with the Adam step over NVLink peer memory (one node, one process per
+ * GPU).  Every rank exposes its flat gradient buffer and a flag block to its peers (CUDA IPC);
+ * one kernel per rank then (1) signals "my gradient is complete" to every peer and waits for
+ * theirs, (2) sums the W peer buffers element by element in rank order — the same order on every
+ * rank, so all ranks compute bit-identical sums and the replicas never drift — and applies the
+ * Adam update of ddqn_adam_step to its own parameter copy, (3) signals "done reading" and waits
+ * for the peers before it exits, so the next backward pass may overwrite the gradient buffers.
+ *   peer_grads : device array [world] of pointers to every rank's gradient buffer (n doubles)
+ *   peer_flags : device array [world] of pointers to every rank's flag block (uint64[2*world],
+ *                zero-initialised); my block is peer_flags[rank]
+ *   sync_state : device uint64[4], zero-initialised: {epoch, blocks-done counter, error, -}
+ * Waits are bounded (~1 s); on timeout sync_state[2] is set to 1 and the kernel returns. */
+/* Map a peer's cudaMalloc allocation into this process for access from the CURRENT device
+ * (cudaIpcOpenMemHandle with lazy peer access; no context is created on the peer's device).
+ * `handle64` is the 64-byte cudaIpcMemHandle_t of the allocation; *out is its base address. */
+int p2p_open_ipc_handle(const unsigned char* handle64, void** out);
+/* The 64-byte cudaIpcMemHandle_t of the cudaMalloc allocation that contains device pointer `ptr`. */
+int p2p_get_ipc_handle(const void* ptr, unsigned char* handle64);
+
+int p2p_allreduce_adam_f64(const double* const* peer_grads, uint64_t* const* peer_flags,
+                           uint64_t* sync_state, int rank, int world, double* params,
+                           double* exp_avg, double* exp_avg_sq, int64_t* step_counter, int64_t n,
+                           double lr, double beta1, double beta2, double eps, void* stream);
+
 /* ---- K0: batched epsilon-greedy ---------------------------------------------------------------- */
 
 /* = epsilon_greedy_policy, src/dqn_lib.py:16-30, for n boards.  With probability eps the action is

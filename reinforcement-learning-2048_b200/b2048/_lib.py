@@ -56,6 +56,11 @@ SIGNATURES = {
     "conv_patches_grad_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ddqn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double,
                                ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
+    "p2p_get_ipc_handle": (c_int, [c_void_p, ctypes.c_char_p]),
+    "p2p_open_ipc_handle": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "p2p_allreduce_adam_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_double, c_void_p]),
     "egreedy_select": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_uint64, c_uint64, c_uint64,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }

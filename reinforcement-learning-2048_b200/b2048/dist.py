@@ -49,12 +49,17 @@ class FlatGrads:
     """One contiguous gradient buffer for a module; every parameter's .grad is a view into it, so
     a single collective moves the whole gradient."""
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, tail: int = 0):
+        """`tail` extra elements are allocated behind the gradients in the SAME allocation
+        (`self.tail`): the peer-memory exchange keeps its flags there so that one IPC handle
+        covers everything a peer needs."""
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise ValueError("module has no trainable parameters")
         self.params = params
-        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+        n = sum(p.numel() for p in params)
+        self.buffer = torch.zeros(n + tail, dtype=params[0].dtype, device=params[0].device)
+        self.flat, self.tail = self.buffer[:n], self.buffer[n:]
         off = 0
         for p in params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)

@@ -19,7 +19,7 @@ from .replay import ReplayRing
 class DDQNUpdater:
     def __init__(self, model: torch.nn.Module, ring: ReplayRing, batch_size: int = 5000, gamma: float = 0.8,
                  lr: float = 1e-2, use_double: bool = True, conv: bool = True, target_model=None,
-                 use_graph: bool = True, seed: int = 2051):
+                 use_graph: bool = True, seed: int = 2051, exchange: str = "p2p"):
         self.model, self.ring = model, ring
         self.target = target_model if target_model is not None else copy.deepcopy(model)
         for p in self.target.parameters():
@@ -31,9 +31,16 @@ class DDQNUpdater:
         bdist.broadcast_module(self.model)
         bdist.broadcast_module(self.target)
         self.params = bdist.FlatParams(model)        # parameters and gradients as two flat buffers:
-        self.grads = bdist.FlatGrads(model)          #   one allreduce, one fused Adam kernel
+        world = bdist.world()[1]
+        use_p2p = world > 1 and exchange == "p2p" and self.device.type == "cuda"
+        self.grads = bdist.FlatGrads(model, tail=2 * world if use_p2p else 0)   # one allreduce, one fused Adam kernel
         self.opt = ddqn.FusedAdam(self.params.flat, self.grads.flat, lr=lr)
         self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        # gradient exchange: "p2p" = fused NVLink allreduce+Adam kernel, "nccl" = all_reduce then Adam
+        self.exchange = None
+        if use_p2p:
+            from .p2p import PeerGradExchange
+            self.exchange = PeerGradExchange(self.grads)
         kw = dict(device=self.device)
         B = self.B
         self.batch = (torch.empty((B, 16), dtype=torch.float64, **kw), torch.empty(B, dtype=torch.int64, **kw),
@@ -67,8 +74,11 @@ class DDQNUpdater:
                                     self.use_double)
         self.grads.zero_()
         loss.backward()
-        self.grads.allreduce_()          # sum over ranks == gradient of the summed loss over the global batch
-        self.opt.step()
+        if self.exchange is not None:    # sum over ranks == gradient of the summed loss over the global batch
+            self.exchange.allreduce_adam(self.opt)
+        else:
+            self.grads.allreduce_()
+            self.opt.step()
         self.loss.copy_(loss.detach())
 
     def update(self) -> torch.Tensor:
