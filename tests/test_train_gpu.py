@@ -195,3 +195,25 @@ def test_checkpoint_resume_is_bit_identical(cuda, tmp_path):
     assert torch.equal(ve2.boards, want[0]) and torch.equal(ring2.s, want[1]) and torch.equal(ring2.head_size, want[2])
     for p, q in zip(up2.model.parameters(), want[3]):
         np.testing.assert_allclose(p.detach().cpu().numpy(), q.cpu().numpy(), rtol=1e-12, atol=1e-14)
+
+
+def test_batched_training_loop_follows_the_reference_schedule(cuda):
+    """training_loop's per-episode rules on 512 concurrent games: one update per finished episode
+    after the warm-up, target syncs at multiples of K, epsilon by episode index."""
+    from b2048.train import TrainConfig, epsilon_for, train_batched
+    cfg = TrainConfig(n_envs=512, replay_buffer_length=15000, batch_size=256, no_episodes=2500,
+                      no_episodes_to_reach_epsilon=1000, no_episodes_before_training=1000,
+                      no_episodes_before_updating_target=500, conv=False, seed=3, max_updates_per_step=64,
+                      use_graph=False)
+    assert epsilon_for(0, cfg) == 1.0 and epsilon_for(500, cfg) == 0.5 and epsilon_for(5000, cfg) == 0.01
+    torch.manual_seed(0)
+    model = dense_model().to(cuda)
+    before = [p.detach().clone() for p in model.parameters()]
+    logs = []
+    out = train_batched(model, cfg, device=cuda, log_every=50, on_log=logs.append)
+    assert out["games"] >= 2500
+    owed = out["games"] - 1001                                   # episodes with index > 1000
+    assert 0 < out["updates"] <= owed and out["updates"] >= owed - 64 * 2
+    assert out["target_syncs"] >= 4                              # episode 0, 500, 1000, 1500, 2000 (several may share a step)
+    assert not any(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    assert logs and logs[-1]["epsilon"] <= logs[0]["epsilon"] and np.isfinite(out["final_loss"])
