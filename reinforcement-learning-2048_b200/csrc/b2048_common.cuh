@@ -16,6 +16,18 @@ namespace b2048 {
 constexpr int LUT_ROWS = 65536;
 constexpr int LUT_SMEM_ROWS = 57344;
 constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
+// The shared-memory copy is stored bank-swizzled: entry i sits at i ^ ((i >> 6) & 31).  The bank of
+// an entry is its low 5 index bits = cell 0 and the low bit of cell 1, and real boards make those
+// very non-uniform (30 % of the synthetic benchmark's cells are empty): 6.3 wavefronts per warp
+// lookup unswizzled, 3.7 swizzled, 3.5 for uniformly random banks (simulated, profiles/bank_sim.py).
+// The XOR only permutes entries inside aligned groups of 32, so the staged range stays contiguous.
+// DeviceCtx::lut holds the plain table [0, 65536) followed by this swizzled copy [65536, +57344).
+#ifndef B2048_V_SWZ
+#define B2048_V_SWZ 1
+#endif
+constexpr int LUT_SWZ_SHIFT = 6;
+constexpr uint32_t LUT_SWZ_MASK = B2048_V_SWZ ? 31u : 0u;
+__host__ __device__ constexpr uint32_t lut_swizzle(uint32_t i) { return i ^ ((i >> LUT_SWZ_SHIFT) & LUT_SWZ_MASK); }
 
 // Philox key domains (xored into the high key word) so that streams never collide.
 enum : uint32_t {
@@ -28,7 +40,7 @@ enum : uint32_t {
 };
 
 struct DeviceCtx {
-  uint32_t* lut = nullptr;       // [65536] row table
+  uint32_t* lut = nullptr;       // [65536] row table + [LUT_SMEM_ROWS] swizzled copy for shared memory
   double* partials = nullptr;    // [MAX_PARTIALS] loss partial sums
   unsigned int* ticket = nullptr;// last-block-done counter
   int sm_count = 0;
@@ -113,16 +125,31 @@ __host__ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t doma
 // below is written to minimise ALU-pipe instructions.  Measured on B200 and NOT adopted: right
 // shifts as IMAD.HI (4-cycle issue on the FMA pipe), the +0x7777.. adds as IMAD (no gain: ptxas
 // already balances plain adds across both pipes), booleans as IMAD.WIDE carries.
+// The "+ 0x7777.." of the carry-free nibble tests, as a functor: plain add (ptxas picks VIADD on the
+// ALU pipe) or, in the streaming kernel, a multiply-add through a run-time 1 (IMAD on the FMA pipe).
+struct Add7 {
+  __device__ __forceinline__ uint32_t operator()(uint32_t x) const { return x + 0x77777777u; }
+};
+struct Add7Fma {
+  uint32_t one;
+  __device__ __forceinline__ uint32_t operator()(uint32_t x) const {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 0x77777777, %2;" : "=r"(r) : "r"(one), "r"(x));
+    return r;
+  }
+};
 // bit 3 of every nibble set iff the nibble is non-zero (carry-free: 7+7 < 16).
-__device__ __forceinline__ uint32_t nz3(uint32_t v) {
-  return (((v & 0x77777777u) + 0x77777777u) | v) & 0x88888888u;
+template <class A = Add7>
+__device__ __forceinline__ uint32_t nz3(uint32_t v, A add = A()) {
+  return (add(v & 0x77777777u) | v) & 0x88888888u;
 }
 // same for a ^ b, WITHOUT the final mask (bits other than bit 3 of each nibble are garbage).
 // Two 3-input LOP3s, written as lop3 so that ptxas does not split the xor out (one ALU op more).
-__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b) {
+template <class A = Add7>
+__device__ __forceinline__ uint32_t ne3_dirty(uint32_t a, uint32_t b, A add = A()) {
   uint32_t t, r;
   asm("lop3.b32 %0, %1, %2, 0x77777777, 0x28;" : "=r"(t) : "r"(a), "r"(b));   // (a ^ b) & 0x7777...
-  t += 0x77777777u;
+  t = add(t);
   asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(r) : "r"(t), "r"(a), "r"(b));   // t | (a ^ b)
   return r;
 }
@@ -157,6 +184,14 @@ __device__ __forceinline__ uint32_t legal_mask(uint32_t lo, uint32_t hi) {
 // byte of a horizontal flip (s = 4, m = 0x0F0F0F0F); for `left` m = 0.  Both halves are
 // involutions, so the inverse is delta-swap first, then the inverse byte permutation.
 // The left shift is stored as a multiplier (mul_l = 2^s) so that it issues as IMAD on the FMA pipe.
+// PRMT with a run-time selector whose nibbles are all < 8.  `__byte_perm` masks the selector with
+// 0x7777 first (an extra LOP3 on the saturated ALU pipe); the raw instruction does not need it.
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
 struct ActXform {
   uint32_t sel_fwd;  // lo selector | hi selector << 16
   uint32_t sel_inv;
@@ -268,8 +303,8 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward,
                                             uint32_t& flags, uint32_t& changed) {
   const ActXform x = tabs->act[a];
-  uint32_t zl = __byte_perm(lo, hi, x.sel_fwd);
-  uint32_t zh = __byte_perm(lo, hi, x.sel_fwd_hi);
+  uint32_t zl = prmt_raw(lo, hi, x.sel_fwd & 0xFFFFu);
+  uint32_t zh = prmt_raw(lo, hi, x.sel_fwd_hi);
   zl = delta_swap(zl, x);
   zh = delta_swap(zh, x);
   uint32_t e0, e1, e2, e3, extra;
@@ -303,17 +338,19 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
 
   wl = delta_swap(wl, x);
   wh = delta_swap(wh, x);
-  olo = __byte_perm(wl, wh, x.sel_inv);
-  ohi = __byte_perm(wl, wh, x.sel_inv_hi);
+  olo = prmt_raw(wl, wh, x.sel_inv & 0xFFFFu);
+  ohi = prmt_raw(wl, wh, x.sel_inv_hi);
 }
 
 // ---- spawn ---------------------------------------------------------------------------------------
 // Put exponent e (0 = nothing) into the k-th empty cell (row-major) where
 // k = floor(w_pos * n_empty / 2^32).  Requires at most 15 empty cells.  `e29` = e << 29.
-__device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint32_t w_pos,
-                                                uint32_t e29) {
-  const uint32_t e3_lo = ~(((lo & 0x77777777u) + 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
-  const uint32_t e3_hi = ~(((hi & 0x77777777u) + 0x77777777u) | hi) & 0x88888888u;
+// Bit 3 of the chosen empty nibble (exactly one bit across both words; none if the board is full).
+template <class A = Add7>
+__device__ __forceinline__ void kth_empty_mask(uint32_t lo, uint32_t hi, uint32_t w_pos, uint32_t& h_lo,
+                                               uint32_t& h_hi, A add = A()) {
+  const uint32_t e3_lo = ~(add(lo & 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
+  const uint32_t e3_hi = ~(add(hi & 0x77777777u) | hi) & 0x88888888u;
   const uint32_t e_lo = (e3_lo >> 3), e_hi = (e3_hi >> 3);
   // inclusive prefix counts per nibble: multiply by 0x11111111 (counts <= 15 never carry)
   const uint32_t p_lo = e_lo * 0x11111111u;
@@ -322,10 +359,16 @@ __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint
   const uint32_t cnt = (p_hi >> 28);
   const uint32_t tgt = __umulhi(w_pos, cnt) * 0x11111111u + 0x11111111u;  // (k+1) in every nibble
   // the chosen nibble is the empty one whose prefix count equals k+1
-  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt) & e3_lo;
-  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt) & e3_hi;
-  // exactly one bit (bit 3 of the chosen nibble) is set across h_lo/h_hi; the cell is empty so + == |
-  // hi32(h * (e << 29)) = (h >> 3) * e: shift, scale and insert in one IMAD.HI each
+  h_lo = ~ne3_dirty(p_lo, tgt, add) & e3_lo;
+  h_hi = ~ne3_dirty(p_hi, tgt, add) & e3_hi;
+}
+template <class A = Add7>
+__device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint32_t w_pos,
+                                                uint32_t e29, A add = A()) {
+  uint32_t h_lo, h_hi;
+  kth_empty_mask(lo, hi, w_pos, h_lo, h_hi, add);
+  // the cell is empty so + == |;  hi32(h * (e << 29)) = (h >> 3) * e: shift, scale and insert in one
+  // IMAD.HI each
   lo = __umulhi(h_lo, e29) + lo;
   hi = __umulhi(h_hi, e29) + hi;
 }

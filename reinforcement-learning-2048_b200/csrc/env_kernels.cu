@@ -54,12 +54,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // Per-board tail shared by the step kernels: spawn one tile iff the move changed the board.
 //   w   : the board's Philox word (position from the high bits, value from the low 16 bits)
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
-template <bool HAS_OVERRIDE>
+template <bool HAS_OVERRIDE, class A = Add7>
 __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
-                                             uint32_t p4, uint32_t ovr, uint32_t& flags) {
+                                             uint32_t p4, uint32_t ovr, uint32_t& flags, A add = A()) {
   const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w, e29);
+    spawn_kth_empty(nlo, nhi, w, e29, add);
   } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
@@ -90,7 +90,38 @@ constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
 #ifndef B2048_FMA_ADDR
 #define B2048_FMA_ADDR 1
 #endif
+#ifndef B2048_V_MAX3
+#define B2048_V_MAX3 1
+#endif
+#ifndef B2048_V_IDPADDR
+#define B2048_V_IDPADDR 1
+#endif
+#ifndef B2048_V_RW2
+#define B2048_V_RW2 1
+#endif
+#ifndef B2048_V_FMAFLAG
+#define B2048_V_FMAFLAG 1
+#endif
+#ifndef B2048_V_ADD7
+#define B2048_V_ADD7 1
+#endif
+#ifndef B2048_V_SHR16
+#define B2048_V_SHR16 1
+#endif
+#if B2048_V_SHR16
+#define SHR16(x) __dp2a_hi((x), 0x01000000u, 0u)   // high half * 1 on the FMA pipe instead of SHF
+#else
+#define SHR16(x) ((x) >> 16)
+#endif
+#ifndef B2048_V_IDPACT
+#define B2048_V_IDPACT 1
+#endif
 
+// c + a * b if v != 0, as a predicated multiply-add
+__device__ __forceinline__ uint32_t pmad(uint32_t v, uint32_t a, uint32_t b, uint32_t c) {
+  asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; @p mad.lo.u32 %0, %2, %3, %0;}" : "+r"(c) : "r"(v), "r"(a), "r"(b));
+  return c;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -117,21 +148,35 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
                                              uint32_t four, uint32_t one) {
   const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
   const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
-  uint32_t zl = __byte_perm(lo, hi, xa.x);
-  uint32_t zh = __byte_perm(lo, hi, xa.y);
+  uint32_t zl = prmt_raw(lo, hi, xa.x);
+  uint32_t zh = prmt_raw(lo, hi, xa.y);
   {
     const uint32_t tl = (zl ^ (zl >> xb.y)) & xb.z, th = (zh ^ (zh >> xb.y)) & xb.z;
     zl ^= tl ^ (tl * xb.x);
     zh ^= th ^ (th * xb.x);
   }
   uint32_t e0, e1, e2, e3, extra = 0;
+#if B2048_V_MAX3
+  // all four rows below LUT_SMEM_ROWS <=> max(zl, zh, limit-1) per 16-bit half == limit-1: VIMNMX3 + ISETP
+  constexpr uint32_t LIM = ((uint32_t)LUT_SMEM_ROWS - 1u) * 0x00010001u;
+  if (__builtin_expect(__vmaxu2(__vmaxu2(zl, zh), LIM) != LIM, 0)) {
+#else
   const uint32_t mx = __vmaxu2(zl, zh);
   if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
+#endif
     const uint4 e = lookup4_global_cold(zl, zh, glut);
     e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
     extra = extra_reward_eeee(zl, zh);
   } else {
-#if B2048_FMA_ADDR
+#if B2048_V_IDPADDR
+    // row * 4 + base as ONE integer dot product (FMA pipe): halves of z times bytes {4,0} / {0,4}
+    const uint32_t sl = zl ^ ((zl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));   // both rows at once
+    const uint32_t sh = zh ^ ((zh >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+    e0 = lds32(__dp2a_lo(sl, 0x04000004u, sbase));
+    e1 = lds32(__dp2a_hi(sl, 0x04000004u, sbase));
+    e2 = lds32(__dp2a_lo(sh, 0x04000004u, sbase));
+    e3 = lds32(__dp2a_hi(sh, 0x04000004u, sbase));
+#elif B2048_FMA_ADDR
     e0 = lds32(__byte_perm(zl, 0u, 0x4410) * four + sbase);   // PRMT (ALU) + IMAD (FMA) per row
     e1 = lds32(__byte_perm(zl, 0u, 0x4432) * four + sbase);
     e2 = lds32(__byte_perm(zh, 0u, 0x4410) * four + sbase);
@@ -148,34 +193,53 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
   const uint32_t fl = h01 | h23;
+#if B2048_V_RW2
+  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, 0x0404u, __dp2a_lo(h01 & 0x3FFF3FFFu, 0x0404u, extra));
+#else
   const uint32_t s = (h01 & 0x3FFF3FFFu) + (h23 & 0x3FFF3FFFu);
   reward = __dp2a_lo(s, 0x0404u, extra);
+#endif
 
   // legality of the input board in the transformed frame (see slide_board)
   const uint32_t changed = (wl ^ zl) | (wh ^ zh);
-  const uint32_t n_l = nz3(zl), n_h = nz3(zh);
-  const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = zh >> 16;
-  const uint32_t ne_l = ne3_dirty(zl, v_l), ne_h = ne3_dirty(zh, v_h);
-  const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = n_h >> 16;
+#if B2048_V_ADD7
+  const Add7Fma add{one};
+#else
+  const Add7 add;
+#endif
+  const uint32_t n_l = nz3(zl, add), n_h = nz3(zh, add);
+  const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = SHR16(zh);
+  const uint32_t ne_l = ne3_dirty(zl, v_l, add), ne_h = ne3_dirty(zh, v_h, add);
+  const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = SHR16(n_h);
   const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
   // table index built on top of the row address with four predicated adds (no SEL, no final add)
   uint32_t fa = sa;
+#if B2048_V_FMAFLAG
+  // predicated multiply-adds through run-time constants: FMA pipe instead of the saturated ALU pipe
+  fa = pmad(changed, one, one, fa);
+  fa = pmad(fl & 0x40004000u, one + one, one, fa);
+  fa = pmad(up, four, one, fa);
+  fa = pmad(dn_l | (dn_h & 0x0000FFFFu), four, one + one, fa);
+  fa = pmad(fl & 0x80008000u, four, four, fa);
+  flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED | OVERFLOW
+#else
   if (changed) fa += 1u;
   if (fl & 0x40004000u) fa += 2u;
   if (up) fa += 4u;
   if (dn_l | (dn_h & 0x0000FFFFu)) fa += 8u;
-  flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED
-  if (fl & 0x80008000u) flags |= B2048_FLAG_OVERFLOW;
+  if (fl & 0x80008000u) fa += 16u;
+  flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED | OVERFLOW
+#endif
 
   {
     const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
     wl ^= tl ^ (tl * xb.x);
     wh ^= th ^ (th * xb.x);
   }
-  olo = __byte_perm(wl, wh, xa.z);
-  ohi = __byte_perm(wl, wh, xa.w);
-  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags);
+  olo = prmt_raw(wl, wh, xa.z);
+  ohi = prmt_raw(wl, wh, xa.w);
+  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags, add);
 }
 
 // ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
@@ -210,7 +274,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   if (threadIdx.x < 128) {
     const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
     smem_raw[SM_LEGAL + threadIdx.x] =
-        (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u));
+        (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
+                  ((m & 16u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -218,7 +283,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     constexpr uint32_t CHUNK = 32768;  // 7 bulk copies of 32 KB
 #pragma unroll
     for (uint32_t off = 0; off < (uint32_t)LUT_SMEM_BYTES; off += CHUNK)
-      bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut) + off, CHUNK, bar);
+      bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut + LUT_ROWS) + off, CHUNK, bar);
   }
 
   // 32-bit quad index (the host wrapper keeps nquads < 2^32): every global address is then one
@@ -270,16 +335,22 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     }
 
     // the four action bytes -> four table-row offsets (action * 32) in one AND + shift
+#if B2048_V_IDPACT
+    const uint32_t a32 = a4 & 0x03030303u;     // byte j * 32 + base = one IDP.4A per board
+#define SA_OF(j) __dp4a(a32, 0x20u << (8 * (j)), sbase)
+#else
     const uint32_t a32 = (a4 & 0x03030303u) << 5;
+#define SA_OF(j) (__byte_perm(a32, 0u, 0x4440 + (j)) * one + sbase)
+#endif
     uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3;
-    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4440) * one + sbase, glut, ba.x, ba.y, w.x, p4,
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), glut, ba.x, ba.y, w.x, p4,
                                o4 & 0xFFu, n0l, n0h, rw0, f0, four, one);
-    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4441) * one + sbase, glut, ba.z, ba.w, w.y, p4,
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), glut, ba.z, ba.w, w.y, p4,
                                (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, four, one);
     st_stream_v4(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h));
-    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4442) * one + sbase, glut, bb.x, bb.y, w.z, p4,
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), glut, bb.x, bb.y, w.z, p4,
                                (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, four, one);
-    stream_board<HAS_OVERRIDE>(sbase, __byte_perm(a32, 0u, 0x4443) * one + sbase, glut, bb.z, bb.w, w.w, p4,
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), glut, bb.z, bb.w, w.w, p4,
                                o4 >> 24, n1l, n1h, rw3, f3, four, one);
     st_stream_v4(next2 + 2u * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));

@@ -123,8 +123,11 @@ extern "C" int b2048_init(int device) {
   c->sm_count = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   const std::vector<uint32_t>& lut = host_lut();
-  if ((e = cudaMalloc(&c->lut, LUT_ROWS * sizeof(uint32_t))) != cudaSuccess) return (int)e;
-  if ((e = cudaMemcpy(c->lut, lut.data(), LUT_ROWS * sizeof(uint32_t), cudaMemcpyHostToDevice)) !=
+  std::vector<uint32_t> both(lut.begin(), lut.end());      // plain table, then the swizzled smem image
+  both.resize(LUT_ROWS + LUT_SMEM_ROWS);
+  for (uint32_t i = 0; i < (uint32_t)LUT_SMEM_ROWS; ++i) both[LUT_ROWS + lut_swizzle(i)] = lut[i];
+  if ((e = cudaMalloc(&c->lut, both.size() * sizeof(uint32_t))) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpy(c->lut, both.data(), both.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) !=
       cudaSuccess)
     return (int)e;
   if ((e = cudaMalloc(&c->partials, MAX_PARTIALS * sizeof(double))) != cudaSuccess) return (int)e;
