@@ -18,7 +18,7 @@ lo, hi = max(((int(re.search(r"0x([0-9a-f]+)", r).group(1), 16), a) for a, p, op
 # cold blocks: forward predicated branches whose fall-through contains a CALL, or uniform BRA.U skipping >40 instrs
 cold = []
 for i, (a, p, op, r) in enumerate(ins):
-    if lo <= a <= hi and op.startswith("BRA") and p:
+    if lo <= a <= hi and op.startswith("BRA") and (p or re.match(r"\s*!?UP\d", r)):
         t = re.search(r"0x([0-9a-f]+)", r)
         if t and int(t.group(1), 16) > a:
             tgt = int(t.group(1), 16)

@@ -297,12 +297,14 @@ __device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t
 // Slide + merge one board by one action, and derive the legal mask of the INPUT board in the
 // transformed frame.  Outputs: slid board (no spawn), reward, flags (legal | done | changed |
 // overflow).
+// tabs == nullptr: the per-action constants are computed instead of read from shared memory (cold
+// paths that have no SmemTabs at hand).
 template <bool SMEM, bool LEGAL = true>
 __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a, const SmemTabs* tabs,
                                             const uint32_t* slut, const uint32_t* __restrict__ glut,
                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward,
                                             uint32_t& flags, uint32_t& changed) {
-  const ActXform x = tabs->act[a];
+  const ActXform x = tabs ? tabs->act[a] : act_xform((int)a);
   uint32_t zl = prmt_raw(lo, hi, x.sel_fwd & 0xFFFFu);
   uint32_t zh = prmt_raw(lo, hi, x.sel_fwd_hi);
   zl = delta_swap(zl, x);
@@ -330,7 +332,7 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
     const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
     const uint32_t m = (changed ? 1u : 0u) | ((fl & 0x40004000u) ? 2u : 0u) | (up ? 4u : 0u) |
                        ((dn_l | (dn_h & 0x0000FFFFu)) ? 8u : 0u);
-    flags = tabs->legal[a][m] | (changed ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
+    flags = (tabs ? (uint32_t)tabs->legal[a][m] : zframe_to_legal((int)a, m)) | (changed ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
             ((fl & 0x80008000u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u);
   } else {
     flags = (fl & 0x80008000u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u;

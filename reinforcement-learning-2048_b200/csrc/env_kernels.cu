@@ -80,48 +80,17 @@ constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 // pointers ptxas re-derived the shared window base (S2R + MOV + LEA) for every board.
 constexpr uint32_t SM_ACT = (uint32_t)LUT_SMEM_BYTES;   // 4 rows x 32 B: per-action transform constants
 constexpr uint32_t SM_LEGAL = SM_ACT + 128;             // 4 rows x 32 B: flags byte per (action, frame mask)
-constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // runtime constants {4, 1, -, -}
+constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // run-time constants {4, 1, 2, 0}
 constexpr uint32_t SM_BAR = SM_CONST + 16;              // mbarrier
 constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
 
-// ptxas turns idx * 4 + base into LEA on the saturated ALU pipe.  Multiplying by a constant it
-// cannot see (4 and 1 read from shared memory at run time) keeps the table addresses IMADs on the
-// FMA pipe, which is ~28 % busy in this kernel (measured: 0.397 -> 0.3895 ms per 64Mi boards).
-#ifndef B2048_FMA_ADDR
-#define B2048_FMA_ADDR 1
-#endif
-#ifndef B2048_V_MAX3
-#define B2048_V_MAX3 1
-#endif
-#ifndef B2048_V_IDPADDR
-#define B2048_V_IDPADDR 1
-#endif
-#ifndef B2048_V_RW2
-#define B2048_V_RW2 1
-#endif
-#ifndef B2048_V_FMAFLAG
-#define B2048_V_FMAFLAG 1
-#endif
-#ifndef B2048_V_ADD7
-#define B2048_V_ADD7 1
-#endif
-#ifndef B2048_V_SHR16
-#define B2048_V_SHR16 1
-#endif
-#if B2048_V_SHR16
-#define SHR16(x) __dp2a_hi((x), 0x01000000u, 0u)   // high half * 1 on the FMA pipe instead of SHF
-#else
-#define SHR16(x) ((x) >> 16)
-#endif
-#ifndef B2048_V_IDPACT
-#define B2048_V_IDPACT 1
-#endif
+// Instruction selection in stream_board follows measurements on B200 (profiles/ubench):
+// the integer ALU pipe (LOP3/SHF/PRMT/ISETP/SEL/VIMNMX) issues one warp instruction per 2 cycles and is
+// the busiest unit, the FMA pipe (IMAD, IDP) has room.  So table addresses and 16-bit extracts are
+// integer dot products (IDP.2A/4A: "half-word * 4 + base" in one FMA-pipe instruction, no PRMT/LEA),
+// the "+0x7777.." of the nibble tests is an IMAD through a run-time 1, and selectors go to PRMT raw.
+#define SHR16(x) __dp2a_hi((x), 0x01000000u, 0u)   // x >> 16 as (high half * 1) on the FMA pipe
 
-// c + a * b if v != 0, as a predicated multiply-add
-__device__ __forceinline__ uint32_t pmad(uint32_t v, uint32_t a, uint32_t b, uint32_t c) {
-  asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; @p mad.lo.u32 %0, %2, %3, %0;}" : "+r"(c) : "r"(v), "r"(a), "r"(b));
-  return c;
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -139,13 +108,19 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // One board of the streaming kernel.  `sa` = shared base + 32 * action (row of both small tables).
-// Same arithmetic as slide_board<true> + finish_board (b2048_common.cuh), specialised for the
+// Same arithmetic as slide_board + finish_board (b2048_common.cuh), specialised for the
 // shared-memory map above; the flags byte incl. CHANGED comes straight from the legal table.
+//
+// There is no branch in here: rows outside the staged part of the table (top cell >= 2^14, never
+// seen in play) are clamped for the lookup and only recorded in `mx`; the caller redoes such a quad
+// on a cold path after its stores (fix_quad).  One basic block per four boards lets ptxas overlap
+// the shared-memory latency of one board with the arithmetic of the others.
+constexpr uint32_t LUT_LIM2 = ((uint32_t)LUT_SMEM_ROWS - 1u) * 0x00010001u;   // last staged row, both halves
 template <bool HAS_OVERRIDE>
-__device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const uint32_t* __restrict__ glut,
+__device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32_t& mx,
                                              uint32_t lo, uint32_t hi, uint32_t w, uint32_t p4, uint32_t ovr,
                                              uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags,
-                                             uint32_t four, uint32_t one) {
+                                             uint32_t one) {
   const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
   const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
   uint32_t zl = prmt_raw(lo, hi, xa.x);
@@ -155,82 +130,43 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
     zl ^= tl ^ (tl * xb.x);
     zh ^= th ^ (th * xb.x);
   }
-  uint32_t e0, e1, e2, e3, extra = 0;
-#if B2048_V_MAX3
-  // all four rows below LUT_SMEM_ROWS <=> max(zl, zh, limit-1) per 16-bit half == limit-1: VIMNMX3 + ISETP
-  constexpr uint32_t LIM = ((uint32_t)LUT_SMEM_ROWS - 1u) * 0x00010001u;
-  if (__builtin_expect(__vmaxu2(__vmaxu2(zl, zh), LIM) != LIM, 0)) {
-#else
-  const uint32_t mx = __vmaxu2(zl, zh);
-  if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
-#endif
-    const uint4 e = lookup4_global_cold(zl, zh, glut);
-    e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
-    extra = extra_reward_eeee(zl, zh);
-  } else {
-#if B2048_V_IDPADDR
-    // row * 4 + base as ONE integer dot product (FMA pipe): halves of z times bytes {4,0} / {0,4}
-    const uint32_t sl = zl ^ ((zl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));   // both rows at once
-    const uint32_t sh = zh ^ ((zh >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+  mx = __vmaxu2(__vmaxu2(zl, zh), mx);         // VIMNMX3: running maximum of every row of the quad
+  uint32_t e0, e1, e2, e3;
+  {
+    const uint32_t cl = __vminu2(zl, LUT_LIM2), ch = __vminu2(zh, LUT_LIM2);
+    // bank swizzle of both rows at once, then row * 4 + base as ONE integer dot product (FMA pipe):
+    // halves of the word times bytes {4,0} / {0,4}
+    const uint32_t sl = cl ^ ((cl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+    const uint32_t sh = ch ^ ((ch >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
     e0 = lds32(__dp2a_lo(sl, 0x04000004u, sbase));
     e1 = lds32(__dp2a_hi(sl, 0x04000004u, sbase));
     e2 = lds32(__dp2a_lo(sh, 0x04000004u, sbase));
     e3 = lds32(__dp2a_hi(sh, 0x04000004u, sbase));
-#elif B2048_FMA_ADDR
-    e0 = lds32(__byte_perm(zl, 0u, 0x4410) * four + sbase);   // PRMT (ALU) + IMAD (FMA) per row
-    e1 = lds32(__byte_perm(zl, 0u, 0x4432) * four + sbase);
-    e2 = lds32(__byte_perm(zh, 0u, 0x4410) * four + sbase);
-    e3 = lds32(__byte_perm(zh, 0u, 0x4432) * four + sbase);
-#else
-    e0 = lds32(sbase + ((zl * 4u) & 0x3FFFCu));
-    e1 = lds32(sbase + __byte_perm(zl, 0u, 0x4432) * 4u);
-    e2 = lds32(sbase + ((zh * 4u) & 0x3FFFCu));
-    e3 = lds32(sbase + __byte_perm(zh, 0u, 0x4432) * 4u);
-#endif
   }
   uint32_t wl = __byte_perm(e0, e1, 0x5410);
   uint32_t wh = __byte_perm(e2, e3, 0x5410);
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
   const uint32_t fl = h01 | h23;
-#if B2048_V_RW2
-  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, 0x0404u, __dp2a_lo(h01 & 0x3FFF3FFFu, 0x0404u, extra));
-#else
-  const uint32_t s = (h01 & 0x3FFF3FFFu) + (h23 & 0x3FFF3FFFu);
-  reward = __dp2a_lo(s, 0x0404u, extra);
-#endif
+  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, 0x0404u, __dp2a_lo(h01 & 0x3FFF3FFFu, 0x0404u, 0u));   // 4 * sum of 14-bit fields
 
   // legality of the input board in the transformed frame (see slide_board)
   const uint32_t changed = (wl ^ zl) | (wh ^ zh);
-#if B2048_V_ADD7
   const Add7Fma add{one};
-#else
-  const Add7 add;
-#endif
   const uint32_t n_l = nz3(zl, add), n_h = nz3(zh, add);
   const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = SHR16(zh);
   const uint32_t ne_l = ne3_dirty(zl, v_l, add), ne_h = ne3_dirty(zh, v_h, add);
   const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = SHR16(n_h);
   const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
-  // table index built on top of the row address with four predicated adds (no SEL, no final add)
+  // table index built on top of the row address with five predicated adds (no SEL, no final add)
   uint32_t fa = sa;
-#if B2048_V_FMAFLAG
-  // predicated multiply-adds through run-time constants: FMA pipe instead of the saturated ALU pipe
-  fa = pmad(changed, one, one, fa);
-  fa = pmad(fl & 0x40004000u, one + one, one, fa);
-  fa = pmad(up, four, one, fa);
-  fa = pmad(dn_l | (dn_h & 0x0000FFFFu), four, one + one, fa);
-  fa = pmad(fl & 0x80008000u, four, four, fa);
-  flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED | OVERFLOW
-#else
   if (changed) fa += 1u;
   if (fl & 0x40004000u) fa += 2u;
   if (up) fa += 4u;
   if (dn_l | (dn_h & 0x0000FFFFu)) fa += 8u;
   if (fl & 0x80008000u) fa += 16u;
   flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED | OVERFLOW
-#endif
 
   {
     const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
@@ -240,6 +176,36 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, const 
   olo = prmt_raw(wl, wh, xa.z);
   ohi = prmt_raw(wl, wh, xa.w);
   finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags, add);
+}
+
+// Cold path of the streaming kernel: recompute the four boards of one quad with the full table in
+// global memory (same arithmetic as step_small_kernel) and overwrite the quad's outputs.
+template <bool HAS_OVERRIDE>
+__device__ __noinline__ void fix_quad(uint32_t quad, const uint4* __restrict__ boards2,
+                                      const uint32_t* __restrict__ actions4, uint4* __restrict__ next2,
+                                      uint4* __restrict__ reward4, uint32_t* __restrict__ flags4,
+                                      const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
+                                      uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
+  const uint64_t* bq = reinterpret_cast<const uint64_t*>(boards2) + 4ull * quad;
+  uint64_t* nq = reinterpret_cast<uint64_t*>(next2) + 4ull * quad;
+  int32_t* rq = reinterpret_cast<int32_t*>(reward4) + 4ull * quad;
+  uint8_t* fq = reinterpret_cast<uint8_t*>(flags4) + 4ull * quad;
+  const uint32_t a4 = actions4[quad], o4 = HAS_OVERRIDE ? override4[quad] : 0xFFFFFFFFu;
+  for (uint32_t j = 0; j < 4; ++j) {
+    const uint64_t bd = bq[j];
+    const uint64_t g = index_base + 4ull * quad + j;
+    const uint64_t pidx = g >> 2;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step,
+                                             (uint32_t)(step >> 32)), keys);
+    const uint32_t w = pick_word(r, (uint32_t)g & 3u);
+    uint32_t nl, nh, rw, f, ch;
+    slide_board<false>((uint32_t)bd, (uint32_t)(bd >> 32), (a4 >> (8 * j)) & 3u, nullptr, nullptr, glut, nl, nh,
+                       rw, f, ch);
+    finish_board<HAS_OVERRIDE>(nl, nh, ch, w, p4, (o4 >> (8 * j)) & 0xFFu, f);
+    nq[j] = ((uint64_t)nh << 32) | nl;
+    rq[j] = (int32_t)rw;
+    fq[j] = (uint8_t)f;
+  }
 }
 
 // ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
@@ -305,7 +271,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
   mbar_wait(bar, 0);
-  const uint32_t four = lds32(sbase + SM_CONST), one = lds32(sbase + SM_CONST + 4);
+  const uint32_t one = lds32(sbase + SM_CONST + 4);   // a 1 that ptxas cannot see (Add7Fma)
 
   while (quad < nq) {
     // prefetch this thread's next quad (stride < 2^18, so the sum cannot wrap for nq < 2^32 - 2^18)
@@ -334,27 +300,24 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       w = make_uint4(t[0], t[1], t[2], t[3]);
     }
 
-    // the four action bytes -> four table-row offsets (action * 32) in one AND + shift
-#if B2048_V_IDPACT
     const uint32_t a32 = a4 & 0x03030303u;     // byte j * 32 + base = one IDP.4A per board
 #define SA_OF(j) __dp4a(a32, 0x20u << (8 * (j)), sbase)
-#else
-    const uint32_t a32 = (a4 & 0x03030303u) << 5;
-#define SA_OF(j) (__byte_perm(a32, 0u, 0x4440 + (j)) * one + sbase)
-#endif
-    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3;
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), glut, ba.x, ba.y, w.x, p4,
-                               o4 & 0xFFu, n0l, n0h, rw0, f0, four, one);
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), glut, ba.z, ba.w, w.y, p4,
-                               (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, four, one);
+    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3, mx = LUT_LIM2;
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), mx, ba.x, ba.y, w.x, p4,
+                               o4 & 0xFFu, n0l, n0h, rw0, f0, one);
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), mx, ba.z, ba.w, w.y, p4,
+                               (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, one);
     st_stream_v4(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h));
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), glut, bb.x, bb.y, w.z, p4,
-                               (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, four, one);
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), glut, bb.z, bb.w, w.w, p4,
-                               o4 >> 24, n1l, n1h, rw3, f3, four, one);
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), mx, bb.x, bb.y, w.z, p4,
+                               (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, one);
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), mx, bb.z, bb.w, w.w, p4,
+                               o4 >> 24, n1l, n1h, rw3, f3, one);
     st_stream_v4(next2 + 2u * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
     flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
+    if (__builtin_expect(mx != LUT_LIM2, 0))   // some row of the quad was clamped: redo it from global memory
+      fix_quad<HAS_OVERRIDE>(quad, boards2, actions4, next2, reward4, flags4, glut, keys, step, index_base, p4,
+                             override4);
 
     ba = na; bb = nb; a4 = an; o4 = on;
     quad = nxt;

@@ -110,19 +110,21 @@ def test_step_matches_oracle_with_philox_spawns(cuda, n, index_base, offset):
     assert np.array_equal(flg.cpu().numpy(), o_flg)
 
 
-def test_step_fifty_percent_fours_and_high_tiles(cuda):
+@pytest.mark.parametrize("index_base,max_exp", [(0, 15), (12345, 15), (3, 14)])
+def test_step_fifty_percent_fours_and_high_tiles(cuda, index_base, max_exp):
     """p4 = 0.5 (the reference's spawn rule) and boards with 16384/32768 tiles (rows
-    that miss the shared-memory table and go to the global one)."""
+    that miss the shared-memory table: the streaming kernel redoes those quads from the global
+    one), also with an index base that is not a multiple of four."""
     n = 1 << 20
-    boards = env.random_boards(n, seed=5, p_empty=0.25, max_exp=15, device=cuda)
+    boards = env.random_boards(n, seed=5, p_empty=0.25, max_exp=max_exp, device=cuda)
     actions = env.random_actions(n, seed=6, device=cuda)
-    nxt, rew, flg = env.step(boards, actions, seed=1, step_index=2, p4=env.P4_FIFTY_PERCENT)
-    o_nxt, o_rew, o_flg = bo.step_packed(u64(boards), actions.cpu().numpy(), seed=1, step=2,
+    nxt, rew, flg = env.step(boards, actions, seed=1, step_index=2, p4=env.P4_FIFTY_PERCENT, index_base=index_base)
+    o_nxt, o_rew, o_flg = bo.step_packed(u64(boards), actions.cpu().numpy(), seed=1, step=2, index_base=index_base,
                                          p4_threshold=env.P4_FIFTY_PERCENT, threads=bo.num_threads())
     f = flg.cpu().numpy()
     assert np.array_equal(f, o_flg)
     ok = (f & 0x40) == 0
-    assert (~ok).sum() > 0                      # some 32768+32768 merges exist and are flagged
+    assert (max_exp < 15) == bool(ok.all())     # 32768+32768 merges exist (max_exp 15) and are flagged
     assert np.array_equal(u64(nxt)[ok], o_nxt[ok])
     assert np.array_equal(rew.cpu().numpy()[ok], o_rew[ok])
 
