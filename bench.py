@@ -66,6 +66,7 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
         self.max_mhz = None
         self.ok = False
+        self.ready = threading.Event()        # set after the first sample (the first NVML query is slow)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -78,6 +79,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         if not self.ok:
+            self.ready.set()
             return
         nv = self.nv
         while not self.stop_flag:
@@ -90,6 +92,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), mhz, rs))
             except Exception:
                 pass
+            self.ready.set()
             time.sleep(self.period)
 
     def summary(self, t0: float, t1: float):
@@ -266,8 +269,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period_s=0.002)
     sampler.start()
+    sampler.ready.wait(timeout=5.0)
     for w in range(args.warmup):
         env.step(boards, actions, seed=SEED_SPAWN, step_index=w, index_base=base, out=out)
     barrier()
@@ -350,8 +354,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--headline-only", action="store_true",
                     help="only the device-resident env-step timing (for ncu launch lists); no e2e / extras / CPU baseline")

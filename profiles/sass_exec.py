@@ -2,7 +2,7 @@
 """Executed-path instruction count of the streaming kernel's loop: the loop body minus the cold
 blocks (global-table fallback, misaligned-index Philox path), per iteration (= 4 boards)."""
 import collections, re, subprocess, sys
-LIB = "reinforcement-learning-2048_b200/b2048/libb2048.so"
+LIB = sys.argv[1] if len(sys.argv) > 1 else "reinforcement-learning-2048_b200/b2048/libb2048.so"
 ALU = ("LOP3", "SHF", "PRMT", "ISETP", "SEL", "IADD3", "VIADD", "LEA", "VIMNMX", "PLOP3", "MOV", "IADD")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 body = next(f for f in re.split(r"\n\s*Function : ", sass) if "step_stream_kernelILb0" in f.split("\n")[0])
