@@ -263,6 +263,23 @@ int egreedy_select(const double* q, const uint8_t* flags, double eps, uint64_t s
                    uint64_t index_base, const uint8_t* override_bytes, uint8_t* actions,
                    double* max_q, int64_t n, void* stream);
 
+/* ---- K6: fused forward of the convolutional Q-network (no gradient) ---------------------------- */
+
+/* = model(state) for the conv config, src/configs/double_dqn_conv.py:19-28
+ * (Conv2d(1,64,2) ReLU Conv2d(64,64,2) ReLU Flatten Linear(256,64) ReLU Linear(64,4), float64), as
+ * called without gradient in epsilon_greedy_policy (src/dqn_lib.py:24-25), Player.play_game
+ * (src/player.py:47) and for Q(s') in train_step (src/dqn_lib.py:126-128).  One kernel, FP64
+ * tensor cores.  Exactly one of `boards` (packed, n) and `states` (float64 [n,16], the layout
+ * replay_sample / b2048_unpack_f64 write) is non-NULL.  scaling (boards only): 0 = exponents as
+ * board.log_scale() (src/board.py:224-231), 1 = tile / largest tile as board.normalized()
+ * (src/board.py:218-222).  Weights are the module's own parameter tensors, contiguous float64:
+ * w1[64,1,2,2] b1[64] w2[64,64,2,2] b2[64] w3[64,256] b3[64] w4[4,64] b4[4].  q: float64 [n,4].
+ * Summation order differs from cuBLAS/cuDNN (agreement ~1e-13 relative). */
+int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scaling, const double* w1,
+                          const double* b1, const double* w2, const double* b2, const double* w3,
+                          const double* b3, const double* w4, const double* b4, double* q, int64_t n,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ the tensor's device and raises if the CUDA extension or a GPU is missing (no CPU
 """
 from . import _lib
 from ._lib import B2048Error, LIB_PATH
-from . import checkpoint, env, replay, ddqn, dist, p2p, player, qnet, rollout, train, trainer
+from . import checkpoint, env, replay, ddqn, dist, p2p, player, qfused, qnet, rollout, train, trainer
 from .env import (FLAG_BADSPAWN, FLAG_CHANGED, FLAG_DONE, FLAG_LEGAL, FLAG_OVERFLOW, P4_FIFTY_PERCENT,
                   P4_TEN_PERCENT, SPAWN_NONE, p4_threshold)
 from .replay import ReplayDeque, ReplayRing

@@ -1,4 +1,4 @@
-"""Batched baselines: the reference's `player.py` policies over many concurrent games.
+"""Batched players: the reference's `player.py` policies over many concurrent games.
 
 `Player.play_game(random_policy=True)` picks uniformly among the LEGAL moves (argmax of
 mask * rand, src/player.py:46-57 — unlike the epsilon branch of dqn_lib, which ignores legality)
@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import env
+from .qfused import FusedConvQ, accelerate_inference
 
 
 class BatchedPlayer:
@@ -64,6 +65,49 @@ class BatchedPlayer:
                          out=(self.next, self.reward, self.flags))
                 self._finish(self.flags, quota)
         return self._stats()
+
+    def _observe(self, scaling: str, conv: bool) -> torch.Tensor:
+        if scaling == "log2":                                    # what training feeds the network (dqn_lib.py:8-13)
+            x = env.unpack_f64(self.boards)
+        elif scaling == "normalized":                            # what player.py feeds it (board.py:218-222)
+            t = env.unpack_tiles(self.boards).to(torch.float64)
+            x = t / t.max(dim=1, keepdim=True).values
+        else:
+            raise ValueError(f"unknown input scaling {scaling!r}")
+        return x.view(self.n, 1, 4, 4) if conv else x
+
+    @torch.no_grad()
+    def _model_actions(self, net, scaling: str, conv: bool) -> torch.Tensor:
+        env.legal_mask(self.boards, out=self.legal)
+        if isinstance(net, FusedConvQ):
+            q = net.forward_boards(self.boards, scaling=scaling)
+        else:
+            q = net(self._observe(scaling, conv))
+        mask = ((self.legal[:, None] & self._bits) != 0).to(q.dtype)
+        return torch.argmax(mask * q, dim=1).to(torch.uint8)   # dead board -> action 0, a no-op
+
+    @torch.no_grad()
+    def model_policy(self, model: torch.nn.Module, n_games: int, scaling: str = "normalized", conv: bool = True) -> dict:
+        """Greedy play with a Q-network: action = argmax(legal_mask * Q(board)) with first-index ties
+        (src/player.py:48-53), every board until it has finished its share of `n_games` games."""
+        net = model if isinstance(model, FusedConvQ) else accelerate_inference(model)
+        stalled = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        quota = -(-n_games // self.n)
+        while int(self.games_done.min().item()) < quota:
+            for _ in range(32):
+                self.t += 1
+                actions = self._model_actions(net, scaling, conv)
+                env.step(self.boards, actions, seed=self.seed, step_index=self.t, p4=self.p4,
+                         out=(self.next, self.reward, self.flags))
+                # argmax(mask * Q) picks an ILLEGAL move (value 0) when every legal Q is negative; the
+                # policy is deterministic, so such a game never moves again — the reference loops
+                # forever there (src/player.py:43-59).  Close it and count it.
+                stuck = (self.flags & (env.FLAG_CHANGED | env.FLAG_DONE)) == 0
+                stalled += stuck & (self.games_done < quota)
+                self._finish(torch.where(stuck, self.flags | env.FLAG_DONE, self.flags), quota)
+        out = self._stats()
+        out["stalled_games"] = int(stalled.sum().item())
+        return out
 
     @torch.no_grad()
     def upleft_baseline(self, n_games: int) -> dict:

@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import ddqn, env
+from .qfused import FusedConvQ
 from .replay import ReplayRing
 
 
@@ -31,6 +32,7 @@ class VectorEnv:
         self.actions = torch.empty(self.n, dtype=torch.uint8, **kw)
         self.max_q = torch.empty(self.n, dtype=torch.float64, **kw)
         self.obs = torch.empty((self.n, 16), dtype=torch.float64, **kw)
+        self.q = torch.empty((self.n, 4), dtype=torch.float64, **kw)
         # per-game accumulators and totals over finished games (all on the device)
         self.ep_score = torch.zeros(self.n, dtype=torch.int64, **kw)
         self.ep_moves = torch.zeros(self.n, dtype=torch.int32, **kw)
@@ -52,7 +54,10 @@ class VectorEnv:
         greedy = model is not None and epsilon < 1.0
         if greedy:
             env.legal_mask(self.boards, out=self.legal)
-            q = model(self.observe()).contiguous()
+            if isinstance(model, FusedConvQ):                # one fused kernel straight from the packed boards
+                q = model.forward_boards(self.boards, out=self.q)
+            else:
+                q = model(self.observe()).contiguous()
             ddqn.egreedy_select(q, self.legal, epsilon, seed=self.seed ^ 0x5EED, ctr=self.t,
                                 index_base=self.index_base, out=(self.actions, self.max_q))
         else:

@@ -69,7 +69,7 @@ def train_batched(model: torch.nn.Module, cfg: TrainConfig, device="cuda", log_e
     episodes = updates = syncs = owed = steps = 0
     last_loss = None
     while episodes < cfg.no_episodes:
-        venv.step(model=updater.f_model, epsilon=epsilon_for(episodes, cfg), replay=ring)
+        venv.step(model=updater.i_model, epsilon=epsilon_for(episodes, cfg), replay=ring)
         steps += 1
         finished = int(venv.totals[0].item())            # one scalar read-back per step
         # one update per finished episode once past the warm-up (src/dqn_lib.py:213)

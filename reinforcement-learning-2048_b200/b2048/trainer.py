@@ -12,6 +12,7 @@ import copy
 import torch
 
 from . import ddqn, dist as bdist
+from .qfused import FusedConvQ, accelerate_inference
 from .qnet import accelerate
 from .replay import ReplayRing
 
@@ -28,6 +29,9 @@ class DDQNUpdater:
         self.device = next(model.parameters()).device
         # same parameter tensors, convolutions evaluated as float64 GEMMs (see qnet.py)
         self.f_model, self.f_target = accelerate(self.model), accelerate(self.target)
+        # no-gradient evaluators (Q(s') here, action selection in the rollout): the fused kernel K6 for
+        # the reference's conv network, else the same GEMM path
+        self.i_model, self.i_target = accelerate_inference(self.model), accelerate_inference(self.target)
         bdist.broadcast_module(self.model)
         bdist.broadcast_module(self.target)
         self.params = bdist.FlatParams(model)        # parameters and gradients as two flat buffers:
@@ -54,6 +58,9 @@ class DDQNUpdater:
     def _shape(self, x):
         return x.view(self.B, 1, 4, 4) if self.conv else x
 
+    def _infer(self, net, x):
+        return net(x) if isinstance(net, FusedConvQ) else net(self._shape(x))
+
     def _update_eager(self):
         states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
                                                                         out=self.batch)
@@ -62,8 +69,8 @@ class DDQNUpdater:
         main = torch.cuda.current_stream(self.device)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side), torch.no_grad():
-            q_next_target = self.f_target(self._shape(next_states))
-            q_next_online = self.f_model(self._shape(next_states)) if self.use_double else None
+            q_next_target = self._infer(self.i_target, next_states)
+            q_next_online = self._infer(self.i_model, next_states) if self.use_double else None
         q_cur = self.f_model(self._shape(states))
         main.wait_stream(self.side)
         if not torch.cuda.is_current_stream_capturing():      # eager mode: tell the allocator about the hand-over

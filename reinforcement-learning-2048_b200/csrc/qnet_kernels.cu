@@ -1,0 +1,230 @@
+// qnet_kernels.cu — K6: the reference's convolutional Q-network, forward only, as ONE kernel.
+//
+// Replaces `model(state)` for the conv config (src/configs/double_dqn_conv.py:19-28:
+// Conv2d(1,64,2) ReLU Conv2d(64,64,2) ReLU Flatten Linear(256,64) ReLU Linear(64,4), float64) where no
+// gradient is needed: action selection in epsilon_greedy_policy (src/dqn_lib.py:24-25), greedy play
+// (src/player.py:47) and the two target-side forwards of train_step (src/dqn_lib.py:126-128).
+// Input is either packed boards (exponents as in board.log_scale(), or tiles / max tile as in
+// board.normalized()) or the float64 [n,16] states the replay ring emits; output is Q[n,4].
+//
+// Per sample the network is 84 480 multiply-adds, 97 % of them in two GEMM-shaped layers:
+//   conv2: [4 positions x 256] x [256 x 64]      fc1: [1 x 256] x [256 x 64]
+// Both run on the FP64 tensor cores (DMMA.8x8x4 via mma.sync.m8n8k4.f64; sm_100a has no tcgen05 path
+// for float64).  One CTA per SM keeps the conv2 weights (128 KB) in shared memory in B-fragment order
+// for the whole launch; a warp owns 4 samples = 16 conv2 rows x 64 columns = 16 accumulator tiles.
+// conv1 (4 multiply-adds per element) is recomputed on the fly as the A fragment of conv2: a thread's
+// fragment element always belongs to the same (sample, conv2 position, kernel tap), so its four board
+// cells stay in registers for the whole K loop and no im2col buffer exists anywhere.  Two warps then
+// pool their 8 samples in shared memory for fc1 (full 8-row tiles, fc1 weights streamed from L2), and
+// one of them finishes with the 64 x 4 output layer on CUDA cores.
+#include "b2048_common.cuh"
+
+namespace b2048 {
+namespace {
+
+constexpr int QC_THREADS = 256;           // 8 warps = 4 warp pairs
+constexpr int QC_TILE = 32;               // samples per CTA iteration (4 per warp)
+constexpr int IN2_STRIDE = 260;           // doubles per pooled sample row: 256 + 4 (bank spread for 64-bit loads)
+
+// shared-memory map (bytes)
+constexpr int QS_W2 = 0;                                      // [64 c1][8 n-tiles][32 lanes] doubles
+constexpr int QS_IN2 = QS_W2 + 64 * 8 * 32 * 8;               // [4 pairs][8 samples][IN2_STRIDE]
+constexpr int QS_OUT3 = QS_IN2 + 4 * 8 * IN2_STRIDE * 8;      // [4 pairs][8 samples][64]
+constexpr int QS_W1B = QS_OUT3 + 4 * 8 * 64 * 8;              // [64 c1][8]: w0 w1 w2 w3 bias - - -
+constexpr int QS_B2 = QS_W1B + 64 * 8 * 8;                    // [64]
+constexpr int QS_B3 = QS_B2 + 64 * 8;                         // [64]
+constexpr int QS_W4 = QS_B3 + 64 * 8;                         // [4][64]
+constexpr int QS_B4 = QS_W4 + 4 * 64 * 8;                     // [4]
+constexpr int QS_BYTES = QS_B4 + 4 * 8;
+
+struct QConvWeights {
+  const double *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4;
+};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void pair_barrier(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+// network input of one cell: exponent (log_scale) or tile / max tile (normalized)
+__device__ __forceinline__ double cell_value(uint64_t bd, int cell, int scaling, int emax) {
+  const int e = (int)((bd >> (4 * cell)) & 15u);
+  if (scaling == 0) return (double)e;
+  if (e == 0) return 0.0;
+  return __longlong_as_double((long long)(1023 + e - emax) << 52);   // 2^(e - emax), exact
+}
+
+__global__ void __launch_bounds__(QC_THREADS, 1)
+    qconv_forward_kernel(const uint64_t* __restrict__ boards, const double* __restrict__ states, int scaling,
+                         const QConvWeights wts, double* __restrict__ q, int64_t n) {
+  extern __shared__ __align__(16) unsigned char qsm[];
+  double* w2f = reinterpret_cast<double*>(qsm + QS_W2);
+  double* in2 = reinterpret_cast<double*>(qsm + QS_IN2);
+  double* out3 = reinterpret_cast<double*>(qsm + QS_OUT3);
+  double* w1b = reinterpret_cast<double*>(qsm + QS_W1B);
+  double* b2s = reinterpret_cast<double*>(qsm + QS_B2);
+  double* b3s = reinterpret_cast<double*>(qsm + QS_B3);
+  double* w4s = reinterpret_cast<double*>(qsm + QS_W4);
+  double* b4s = reinterpret_cast<double*>(qsm + QS_B4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, wip = warp & 1;
+  const int fr = lane >> 2, fk = lane & 3;     // fragment row (A, C) / column (B) and k index
+
+  // ---- stage the weights: conv2 in B-fragment order, the small ones as they are --------------------
+  // B fragment of mma.m8n8k4 (col): lane holds B[k = lane % 4][n = lane / 4];  k-step = c1, k = tap,
+  // n-tile nt covers output channels nt*8 .. nt*8+7:  w2f[(c1*8 + nt)*32 + lane] = W2[nt*8 + lane/4][c1*4 + lane%4]
+  for (int i = tid; i < 64 * 8 * 32; i += QC_THREADS) {
+    const int l = i & 31, nt = (i >> 5) & 7, c1 = i >> 8;
+    w2f[i] = __ldg(wts.w2 + (nt * 8 + (l >> 2)) * 256 + c1 * 4 + (l & 3));
+  }
+  for (int i = tid; i < 64 * 8; i += QC_THREADS) {
+    const int c1 = i >> 3, j = i & 7;
+    w1b[i] = j < 4 ? __ldg(wts.w1 + c1 * 4 + j) : (j == 4 ? __ldg(wts.b1 + c1) : 0.0);
+  }
+  if (tid < 64) {
+    b2s[tid] = __ldg(wts.b2 + tid);
+    b3s[tid] = __ldg(wts.b3 + tid);
+  }
+  for (int i = tid; i < 4 * 64; i += QC_THREADS) w4s[i] = __ldg(wts.w4 + i);
+  if (tid < 4) b4s[tid] = __ldg(wts.b4 + tid);
+  __syncthreads();
+
+  // this thread's conv2 row is (sample, position qp) with tap fk: the conv1 output it needs sits at
+  // (qy + ky, qx + kx) of the 3x3 map, and covers board cells (py + jy, px + jx)
+  const int qp = fr & 3, py = (qp >> 1) + (fk >> 1), px = (qp & 1) + (fk & 1);
+  const int cell0 = py * 4 + px;                       // cells cell0, +1, +4, +5
+  double* in2p = in2 + pair * 8 * IN2_STRIDE;
+  double* out3p = out3 + pair * 8 * 64;
+
+  const int64_t tiles = (n + QC_TILE - 1) / QC_TILE;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t s_warp = tile * QC_TILE + warp * 4;  // first of this warp's 4 samples
+    // ---- inputs: 4 cells for each of the two row tiles (samples 0,1 and 2,3 of the warp) ------------
+    double x[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int64_t s = s_warp + mt * 2 + (fr >> 2);
+      if (s < n) {
+        if (boards) {
+          const uint64_t bd = boards[s];
+          int emax = 0;
+          if (scaling != 0) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) emax = max(emax, (int)((bd >> (4 * c)) & 15u));
+          }
+          x[mt][0] = cell_value(bd, cell0, scaling, emax);
+          x[mt][1] = cell_value(bd, cell0 + 1, scaling, emax);
+          x[mt][2] = cell_value(bd, cell0 + 4, scaling, emax);
+          x[mt][3] = cell_value(bd, cell0 + 5, scaling, emax);
+        } else {
+          const double* st = states + 16 * s + cell0;
+          x[mt][0] = __ldg(st); x[mt][1] = __ldg(st + 1); x[mt][2] = __ldg(st + 4); x[mt][3] = __ldg(st + 5);
+        }
+      } else {
+        x[mt][0] = x[mt][1] = x[mt][2] = x[mt][3] = 0.0;
+      }
+    }
+
+    // ---- conv1 (on the fly) + conv2: 16 rows x 64 columns per warp, K = 64 channels x 4 taps --------
+    double acc[2][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll 2
+    for (int c1 = 0; c1 < 64; ++c1) {
+      const double4 w = *reinterpret_cast<const double4*>(w1b + c1 * 8);
+      const double bias = w1b[c1 * 8 + 4];
+      const double a0 = fmax(fma(x[0][3], w.w, fma(x[0][2], w.z, fma(x[0][1], w.y, fma(x[0][0], w.x, bias)))), 0.0);
+      const double a1 = fmax(fma(x[1][3], w.w, fma(x[1][2], w.z, fma(x[1][1], w.y, fma(x[1][0], w.x, bias)))), 0.0);
+      const double* bf = w2f + c1 * 256 + lane;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const double b = bf[nt * 32];
+        dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
+        dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
+      }
+    }
+    // ---- bias + ReLU, pooled per warp pair in nn.Flatten order (channel * 4 + position) ------------
+    // C fragment: lane holds C[row = lane / 4][col = 2 * (lane % 4) + {0,1}]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      double* row = in2p + (wip * 4 + mt * 2 + (fr >> 2)) * IN2_STRIDE + qp;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c2 = nt * 8 + 2 * fk;
+        row[c2 * 4] = fmax(acc[mt][nt][0] + b2s[c2], 0.0);
+        row[c2 * 4 + 4] = fmax(acc[mt][nt][1] + b2s[c2 + 1], 0.0);
+      }
+    }
+    pair_barrier(pair);
+
+    // ---- fc1: 8 pooled samples x 32 of the 64 hidden units per warp, K = 256 ----------------------
+    double h[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) h[nt][0] = h[nt][1] = 0.0;
+    const double* arow = in2p + fr * IN2_STRIDE + fk;
+    const double* brow = wts.w3 + (int64_t)(wip * 32 + fr) * 256 + fk;   // + nt * 8 rows
+#pragma unroll 8
+    for (int ks = 0; ks < 64; ++ks) {
+      const double a = arow[ks * 4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma(h[nt][0], h[nt][1], a, __ldg(brow + nt * 8 * 256 + ks * 4));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int hh = wip * 32 + nt * 8 + 2 * fk;
+      out3p[fr * 64 + hh] = fmax(h[nt][0] + b3s[hh], 0.0);
+      out3p[fr * 64 + hh + 1] = fmax(h[nt][1] + b3s[hh + 1], 0.0);
+    }
+    pair_barrier(pair);
+
+    // ---- output layer: 8 samples x 4 actions on the first warp of the pair ---------------------------
+    if (wip == 0) {
+      const int sl = lane >> 2, a = lane & 3;
+      const int64_t s = tile * QC_TILE + pair * 8 + sl;
+      double v = b4s[a];
+      const double* o = out3p + sl * 64;
+      const double* w = w4s + a * 64;
+#pragma unroll 16
+      for (int k = 0; k < 64; ++k) v = fma(o[k], w[k], v);
+      if (s < n) q[4 * s + a] = v;
+    }
+    // The next tile's stores into in2 / out3 are ordered behind these reads by its own barriers: a warp
+    // reaches barrier 1 of tile t+1 only after its fc1 / output reads of tile t, and nothing is
+    // written to out3 before that barrier or to in2 before the partner has passed barrier 2 of tile t.
+  }
+}
+
+}  // namespace
+
+cudaError_t qnet_kernels_configure() {
+  return cudaFuncSetAttribute(qconv_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_BYTES);
+}
+
+}  // namespace b2048
+
+using namespace b2048;
+
+extern "C" int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scaling, const double* w1,
+                                     const double* b1, const double* w2, const double* b2, const double* w3,
+                                     const double* b3, const double* w4, const double* b4, double* q, int64_t n,
+                                     void* stream) {
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  if (n < 0 || (n > 0 && (!q || (!boards && !states) || (boards && states))) || scaling < 0 || scaling > 1 ||
+      !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4)
+    return B2048_EINVAL;
+  if (n == 0) return B2048_OK;
+  const int64_t tiles = (n + QC_TILE - 1) / QC_TILE;
+  const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
+  qconv_forward_kernel<<<grid, QC_THREADS, QS_BYTES, static_cast<cudaStream_t>(stream)>>>(boards, states, scaling, w,
+                                                                                         q, n);
+  return (int)cudaGetLastError();
+}

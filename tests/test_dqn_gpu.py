@@ -175,3 +175,66 @@ def test_egreedy_matches_reference(cuda, golden_dir):
     ao, mo = do.egreedy_batch(qb.cpu().numpy()[:2000], fb.cpu().numpy()[:2000], np.full(2000, 0x80, np.uint8))
     keep = (~explored & (qb.max(dim=1).values != 0))[:2000].cpu().numpy()
     assert np.array_equal(actm.cpu().numpy()[:2000][keep], ao[keep])
+
+
+# ---- K6: fused conv Q-network forward -----------------------------------------------------------------
+def _conv_net(d, prefix, cuda):
+    from test_shim_gpu import conv_model
+    net = conv_model()
+    net.load_state_dict({k[len(prefix):]: torch.from_numpy(d[k]) for k in d.files if k.startswith(prefix)})
+    return net.to(cuda)
+
+
+def test_fused_conv_forward_matches_reference_q_values(cuda, golden_dir):
+    """K6 against the Q tensors the reference's train_step computed with its own weights on its own
+    sampled batch (tests/golden/dqn_conv.npz): states -> Q(s), next_states -> Q(s') for both networks.
+    Tolerance 1e-9 relative to the largest |Q| (float64, different summation order)."""
+    d = np.load(os.path.join(golden_dir, "dqn_conv.npz"))
+    online, target = _conv_net(d, "w_", cuda), _conv_net(d, "tw_", cuda)
+    fo, ft = b2048.qfused.FusedConvQ(online), b2048.qfused.FusedConvQ(target)
+    s, s2 = torch.from_numpy(d["states"]).to(cuda), torch.from_numpy(d["next_states"]).to(cuda)
+    for got, want in ((fo(s), d["q_cur"]), (fo(s2), d["q_next_online"]), (ft(s2), d["q_next_target"])):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-9 * np.abs(want).max())
+    # packed boards in, exponent scaling == the float64 states the reference builds with log_scale()
+    packed = dev_boards((2 ** d["next_states"].astype(np.int64)) * (d["next_states"] > 0), cuda)
+    np.testing.assert_allclose(fo.forward_boards(packed).cpu().numpy(), d["q_next_online"], rtol=0,
+                               atol=1e-9 * np.abs(d["q_next_online"]).max())
+
+
+@pytest.mark.parametrize("n", [1, 3, 31, 32, 33, 257, 4736, 70001])
+def test_fused_conv_forward_sizes_and_scalings(cuda, n):
+    """Ragged sizes (partial tiles, partial warp pairs, more tiles than SMs) and both input scalings
+    against the torch float64 module on the same inputs."""
+    from test_shim_gpu import conv_model
+    torch.manual_seed(n)
+    net = conv_model().to(cuda)
+    fq = b2048.qfused.FusedConvQ(net)
+    boards = env.random_boards(n, seed=77, p_empty=0.3, max_exp=15, device=cuda)
+    x_log = env.unpack_f64(boards, conv=True)
+    tiles = env.unpack_tiles(boards).to(torch.float64)
+    x_norm = (tiles / tiles.max(dim=1, keepdim=True).values).view(n, 1, 4, 4)
+    with torch.no_grad():
+        for scaling, x in (("log2", x_log), ("normalized", x_norm)):
+            want = net(x)
+            got = fq.forward_boards(boards, scaling=scaling)
+            tol = 1e-9 * float(want.abs().max())
+            assert float((got - want).abs().max()) <= tol, (scaling, float((got - want).abs().max()), tol)
+            assert float((fq(x.contiguous()) - want).abs().max()) <= tol
+    # the kernel reads the module's parameters at call time: an in-place weight change is seen
+    with torch.no_grad():
+        net[7].bias.add_(1.0)
+        assert float((fq.forward_boards(boards) - net(x_log)).abs().max()) <= 1e-9 * float(net(x_log).abs().max())
+
+
+def test_fused_conv_forward_rejects_other_networks(cuda):
+    from test_shim_gpu import conv_model, dense_model
+    assert not b2048.qfused.matches(dense_model().to(cuda))
+    assert not b2048.qfused.matches(conv_model())                      # CPU module
+    assert not b2048.qfused.matches(conv_model().float().to(cuda))     # float32
+    with pytest.raises(ValueError):
+        b2048.qfused.FusedConvQ(dense_model().to(cuda))
+    assert isinstance(b2048.qfused.accelerate_inference(conv_model().to(cuda)), b2048.qfused.FusedConvQ)
+    fq = b2048.qfused.FusedConvQ(conv_model().to(cuda))
+    with pytest.raises(ValueError):
+        fq.forward_boards(env.random_boards(8, device=cuda), scaling="sqrt")
+    assert fq.forward_boards(torch.empty(0, dtype=torch.int64, device=cuda)).shape == (0, 4)

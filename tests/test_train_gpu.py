@@ -165,6 +165,37 @@ def test_batched_player_baselines(cuda):
     assert ul["mean_merge_score"] > 300
 
 
+def test_batched_player_model_policy(cuda):
+    """Player.play_game(random_policy=False) at scale (src/player.py:40-64): argmax(mask * Q) on the
+    board divided by its largest tile, checked per decision against numpy and run to the end."""
+    from b2048.player import BatchedPlayer
+    torch.manual_seed(7)
+    net = conv_model().to(cuda)
+    pl = BatchedPlayer(2048, device=cuda, seed=5)
+    for _ in range(20):                                   # a few random moves so that boards differ
+        pl.t += 1
+        pl.boards = b2048.env.step(pl.boards, b2048.env.random_actions(pl.n, seed=pl.t, device=cuda), seed=5,
+                                   step_index=pl.t)[0]
+    got = pl._model_actions(b2048.qnet.accelerate(net), "normalized", True).cpu().numpy()
+    fused = pl._model_actions(b2048.qfused.FusedConvQ(net), "normalized", True).cpu().numpy()
+    tiles = b2048.env.unpack_tiles(pl.boards).cpu().numpy().astype(np.float64)
+    x = torch.from_numpy(tiles / tiles.max(axis=1, keepdims=True)).view(-1, 1, 4, 4)
+    with torch.no_grad():
+        q = net.cpu()(x).numpy()
+    legal = bo.legal_mask_packed(pl.boards.cpu().numpy().view(np.uint64))
+    mask = ((legal[:, None] >> np.arange(4)) & 1).astype(np.float64)
+    margin = np.sort(mask * q, axis=1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-9       # skip numerically tied decisions
+    assert clear.mean() > 0.9
+    assert np.array_equal(got[clear], np.argmax(mask * q, axis=1)[clear])
+    assert np.array_equal(fused[clear], np.argmax(mask * q, axis=1)[clear])
+    net.to(cuda)
+    st = pl.model_policy(net, 2048)
+    assert st["games"] == 2048 and st["mean_moves"] >= 1 and 0 <= st["stalled_games"] <= 2048, st
+    with pytest.raises(ValueError):
+        pl._observe("sqrt", True)
+
+
 def test_checkpoint_resume_is_bit_identical(cuda, tmp_path):
     """Save mid-run, keep going, reload, redo: same boards, same replay contents, same weights."""
     from b2048 import checkpoint
