@@ -230,6 +230,30 @@ def secondary_metrics(args, dev, rank, world, barrier):
     out["rollout_random_policy"] = {"workload": "4Mi concurrent games per GPU, random policy, replay ring 15000, auto-reset",
                                     "env_steps_per_sec": world * nv / (ms * 1e-3), "ms_per_step": ms}
 
+    # K6: the conv Q-network's no-gradient forward as one fused FP64 tensor-core kernel, alone and inside
+    # an epsilon-greedy rollout step (legal mask -> Q -> action -> env step -> replay append -> reset)
+    torch.manual_seed(0)
+    qnet = conv_qnet().to(dev)
+    fq = b2048.qfused.FusedConvQ(qnet)
+    nq = 1 << 20
+    bq = env.random_boards(nq, seed=SEED_BOARDS, index_base=rank * nq, device=dev)
+    qo = torch.empty((nq, 4), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        fq.forward_boards(bq, out=qo)
+    ms = timed(lambda i: fq.forward_boards(bq, out=qo), 10)
+    out["qnet_forward_conv_fused"] = {
+        "workload": "conv Q-net float64 forward of 1Mi packed boards per GPU, one kernel (DMMA), 168 960 flop/board",
+        "boards_per_sec": world * nq / (ms * 1e-3), "ms_per_launch": ms, "fp64_TFLOPs_per_gpu": nq * 168960 / (ms * 1e-3) / 1e12}
+    ng = 1 << 20
+    vg = VectorEnv(ng, device=dev, seed=5, index_base=rank * ng)
+    for _ in range(3):
+        vg.step(model=fq, epsilon=0.1, replay=ring)
+    ms = timed(lambda i: vg.step(model=fq, epsilon=0.1, replay=ring), 10)
+    out["rollout_egreedy_conv"] = {"workload": "1Mi concurrent games per GPU, epsilon-greedy (0.1) on the conv Q-net via the fused "
+                                               "forward, replay ring 15000, auto-reset",
+                                   "env_steps_per_sec": world * ng / (ms * 1e-3), "ms_per_step": ms}
+    del vg, bq, qo
+
     for name, net, conv in (("conv", conv_qnet, True), ("dense", dense_qnet, False)):
         torch.manual_seed(0)
         up = DDQNUpdater(net().to(dev), ring, batch_size=5000, gamma=0.8, lr=1e-2, conv=conv, use_graph=True)

@@ -15,8 +15,10 @@
 // conv1 (4 multiply-adds per element) is recomputed on the fly as the A fragment of conv2: a thread's
 // fragment element always belongs to the same (sample, conv2 position, kernel tap), so its four board
 // cells stay in registers for the whole K loop and no im2col buffer exists anywhere.  Two warps then
-// pool their 8 samples in shared memory for fc1 (full 8-row tiles, fc1 weights streamed from L2), and
-// one of them finishes with the 64 x 4 output layer on CUDA cores.
+// pool their 8 samples in shared memory for fc1 (full 8-row tiles, fc1 weights streamed from L2 through
+// double-buffered register blocks); the 64 x 4 output layer is 8 FMAs per lane and action plus shuffles.
+// DFMA/DADD/DSETP share the FP64 pipe with DMMA, so biases are folded into the accumulator
+// initialisation and ReLU is done with integer instructions.
 #include "b2048_common.cuh"
 
 namespace b2048 {
@@ -24,13 +26,14 @@ namespace {
 
 constexpr int QC_THREADS = 256;           // 8 warps = 4 warp pairs
 constexpr int QC_TILE = 32;               // samples per CTA iteration (4 per warp)
+constexpr int FC1_BLK = 8;                // k-steps per register block of fc1 weights
 constexpr int IN2_STRIDE = 260;           // doubles per pooled sample row: 256 + 4 (bank spread for 64-bit loads)
 
 // shared-memory map (bytes)
 constexpr int QS_W2 = 0;                                      // [64 c1][8 n-tiles][32 lanes] doubles
 constexpr int QS_IN2 = QS_W2 + 64 * 8 * 32 * 8;               // [4 pairs][8 samples][IN2_STRIDE]
-constexpr int QS_OUT3 = QS_IN2 + 4 * 8 * IN2_STRIDE * 8;      // [4 pairs][8 samples][64]
-constexpr int QS_W1B = QS_OUT3 + 4 * 8 * 64 * 8;              // [64 c1][8]: w0 w1 w2 w3 bias - - -
+constexpr int QS_QPART = QS_IN2 + 4 * 8 * IN2_STRIDE * 8;     // [4 pairs][8 samples][4 actions]: second warp's partial Q
+constexpr int QS_W1B = QS_QPART + 4 * 8 * 4 * 8;              // [64 c1][8]: w0 w1 w2 w3 bias - - -
 constexpr int QS_B2 = QS_W1B + 64 * 8 * 8;                    // [64]
 constexpr int QS_B3 = QS_B2 + 64 * 8;                         // [64]
 constexpr int QS_W4 = QS_B3 + 64 * 8;                         // [4][64]
@@ -45,6 +48,13 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+// max(v, 0) with integer instructions (the FP64 pipe is shared with DMMA and is the bottleneck):
+// clear everything when the sign bit is set.  -0.0 -> +0.0, NaN stays NaN.
+__device__ __forceinline__ double relu(double v) {
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int keep = ~(hi >> 31);
+  return __hiloint2double(hi & keep, lo & keep);
 }
 __device__ __forceinline__ void pair_barrier(int pair) {
   asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
@@ -64,7 +74,7 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   extern __shared__ __align__(16) unsigned char qsm[];
   double* w2f = reinterpret_cast<double*>(qsm + QS_W2);
   double* in2 = reinterpret_cast<double*>(qsm + QS_IN2);
-  double* out3 = reinterpret_cast<double*>(qsm + QS_OUT3);
+  double* qpart = reinterpret_cast<double*>(qsm + QS_QPART);
   double* w1b = reinterpret_cast<double*>(qsm + QS_W1B);
   double* b2s = reinterpret_cast<double*>(qsm + QS_B2);
   double* b3s = reinterpret_cast<double*>(qsm + QS_B3);
@@ -98,7 +108,7 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   const int qp = fr & 3, py = (qp >> 1) + (fk >> 1), px = (qp & 1) + (fk & 1);
   const int cell0 = py * 4 + px;                       // cells cell0, +1, +4, +5
   double* in2p = in2 + pair * 8 * IN2_STRIDE;
-  double* out3p = out3 + pair * 8 * 64;
+  double* qpartp = qpart + pair * 32;
 
   const int64_t tiles = (n + QC_TILE - 1) / QC_TILE;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -130,17 +140,19 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
     }
 
     // ---- conv1 (on the fly) + conv2: 16 rows x 64 columns per warp, K = 64 channels x 4 taps --------
+    // accumulators start at the bias: C fragment, lane holds C[row = lane / 4][col = 2 * (lane % 4) + {0,1}]
     double acc[2][8][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int nt = 0; nt < 8; ++nt) {
+      acc[0][nt][0] = acc[1][nt][0] = b2s[nt * 8 + 2 * fk];
+      acc[0][nt][1] = acc[1][nt][1] = b2s[nt * 8 + 2 * fk + 1];
+    }
 #pragma unroll 2
     for (int c1 = 0; c1 < 64; ++c1) {
       const double4 w = *reinterpret_cast<const double4*>(w1b + c1 * 8);
       const double bias = w1b[c1 * 8 + 4];
-      const double a0 = fmax(fma(x[0][3], w.w, fma(x[0][2], w.z, fma(x[0][1], w.y, fma(x[0][0], w.x, bias)))), 0.0);
-      const double a1 = fmax(fma(x[1][3], w.w, fma(x[1][2], w.z, fma(x[1][1], w.y, fma(x[1][0], w.x, bias)))), 0.0);
+      const double a0 = relu(fma(x[0][3], w.w, fma(x[0][2], w.z, fma(x[0][1], w.y, fma(x[0][0], w.x, bias)))));
+      const double a1 = relu(fma(x[1][3], w.w, fma(x[1][2], w.z, fma(x[1][1], w.y, fma(x[1][0], w.x, bias)))));
       const double* bf = w2f + c1 * 256 + lane;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -149,54 +161,77 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
         dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
       }
     }
-    // ---- bias + ReLU, pooled per warp pair in nn.Flatten order (channel * 4 + position) ------------
-    // C fragment: lane holds C[row = lane / 4][col = 2 * (lane % 4) + {0,1}]
+    // first block of fc1 weights: issued now so that the L2 latency hides behind the epilogue + barrier
+    const double* brow = wts.w3 + (int64_t)(wip * 32 + fr) * 256 + fk;   // B[k = fk][n = fr] of n-tile 0, k-step 0
+    double wb[2][FC1_BLK][4];
+#pragma unroll
+    for (int ks = 0; ks < FC1_BLK; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) wb[0][ks][nt] = __ldg(brow + nt * 8 * 256 + ks * 4);
+    // ---- ReLU, pooled per warp pair in nn.Flatten order (channel * 4 + position) ---------------------
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       double* row = in2p + (wip * 4 + mt * 2 + (fr >> 2)) * IN2_STRIDE + qp;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int c2 = nt * 8 + 2 * fk;
-        row[c2 * 4] = fmax(acc[mt][nt][0] + b2s[c2], 0.0);
-        row[c2 * 4 + 4] = fmax(acc[mt][nt][1] + b2s[c2 + 1], 0.0);
+        row[c2 * 4] = relu(acc[mt][nt][0]);
+        row[c2 * 4 + 4] = relu(acc[mt][nt][1]);
       }
     }
     pair_barrier(pair);
 
-    // ---- fc1: 8 pooled samples x 32 of the 64 hidden units per warp, K = 256 ----------------------
+    // ---- fc1: 8 pooled samples x 32 of the 64 hidden units per warp, K = 256; the weights stream from
+    // L2 through two register blocks of FC1_BLK k-steps (load block j+1 while block j multiplies) ------
     double h[4][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) h[nt][0] = h[nt][1] = 0.0;
-    const double* arow = in2p + fr * IN2_STRIDE + fk;
-    const double* brow = wts.w3 + (int64_t)(wip * 32 + fr) * 256 + fk;   // + nt * 8 rows
-#pragma unroll 8
-    for (int ks = 0; ks < 64; ++ks) {
-      const double a = arow[ks * 4];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma(h[nt][0], h[nt][1], a, __ldg(brow + nt * 8 * 256 + ks * 4));
+    for (int nt = 0; nt < 4; ++nt) {
+      h[nt][0] = b3s[wip * 32 + nt * 8 + 2 * fk];
+      h[nt][1] = b3s[wip * 32 + nt * 8 + 2 * fk + 1];
     }
+    const double* arow = in2p + fr * IN2_STRIDE + fk;
+#pragma unroll
+    for (int blk = 0; blk < 64 / FC1_BLK; ++blk) {
+      if (blk + 1 < 64 / FC1_BLK) {
+#pragma unroll
+        for (int ks = 0; ks < FC1_BLK; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            wb[(blk + 1) & 1][ks][nt] = __ldg(brow + nt * 8 * 256 + ((blk + 1) * FC1_BLK + ks) * 4);
+      }
+#pragma unroll
+      for (int ks = 0; ks < FC1_BLK; ++ks) {
+        const double a = arow[(blk * FC1_BLK + ks) * 4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(h[nt][0], h[nt][1], a, wb[blk & 1][ks][nt]);
+      }
+    }
+
+    // ---- output layer: each lane owns 8 hidden units of one sample; 4 partial dot products, summed
+    // over the 4 lanes of the sample by shuffles and over the two warps of the pair through 256 B ------
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int hh = wip * 32 + nt * 8 + 2 * fk;
-      out3p[fr * 64 + hh] = fmax(h[nt][0] + b3s[hh], 0.0);
-      out3p[fr * 64 + hh + 1] = fmax(h[nt][1] + b3s[hh + 1], 0.0);
+      const double v0 = relu(h[nt][0]), v1 = relu(h[nt][1]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) part[a] = fma(v1, w4s[a * 64 + hh + 1], fma(v0, w4s[a * 64 + hh], part[a]));
     }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      part[a] += __shfl_xor_sync(0xFFFFFFFFu, part[a], 1);
+      part[a] += __shfl_xor_sync(0xFFFFFFFFu, part[a], 2);
+    }
+    const double mine = fk == 0 ? part[0] : fk == 1 ? part[1] : fk == 2 ? part[2] : part[3];   // action fk of sample fr
+    if (wip == 1) qpartp[lane] = mine;
     pair_barrier(pair);
-
-    // ---- output layer: 8 samples x 4 actions on the first warp of the pair ---------------------------
     if (wip == 0) {
-      const int sl = lane >> 2, a = lane & 3;
-      const int64_t s = tile * QC_TILE + pair * 8 + sl;
-      double v = b4s[a];
-      const double* o = out3p + sl * 64;
-      const double* w = w4s + a * 64;
-#pragma unroll 16
-      for (int k = 0; k < 64; ++k) v = fma(o[k], w[k], v);
-      if (s < n) q[4 * s + a] = v;
+      const int64_t s = tile * QC_TILE + pair * 8 + fr;
+      if (s < n) q[4 * s + fk] = mine + qpartp[lane] + b4s[fk];
     }
-    // The next tile's stores into in2 / out3 are ordered behind these reads by its own barriers: a warp
-    // reaches barrier 1 of tile t+1 only after its fc1 / output reads of tile t, and nothing is
-    // written to out3 before that barrier or to in2 before the partner has passed barrier 2 of tile t.
+    // Reuse across tiles is ordered by the barriers themselves: a warp stores into in2 for tile t+1 only
+    // after barrier 2 of tile t, which its partner reaches after its last in2 read; qpart of tile t+1 is
+    // written after barrier 1 of tile t+1, which the first warp reaches after reading qpart of tile t.
   }
 }
 
