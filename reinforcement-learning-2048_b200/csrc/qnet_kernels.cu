@@ -26,6 +26,9 @@ namespace {
 
 constexpr int QC_THREADS = 256;           // 8 warps = 4 warp pairs
 constexpr int QC_TILE = 32;               // samples per CTA iteration (4 per warp)
+#ifndef QC_STAGGER
+#define QC_STAGGER 20000                  // cycles; 0 disables
+#endif
 constexpr int FC1_BLK = 8;                // k-steps per register block of fc1 weights
 constexpr int IN2_STRIDE = 260;           // doubles per pooled sample row: 256 + 4 (bank spread for 64-bit loads)
 
@@ -111,6 +114,15 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   double* qpartp = qpart + pair * 32;
 
   const int64_t tiles = (n + QC_TILE - 1) / QC_TILE;
+#if QC_STAGGER
+  // Each scheduler hosts one warp of pairs 0/1 and one of pairs 2/3.  Left alone they run conv2 (DMMA
+  // bound) and epilogue + fc1 (latency bound) in lockstep; starting pairs 2/3 a third of a tile later
+  // lets one warp's DMMA stream cover the other's epilogue.  Only worth it for long launches.
+  if (pair >= 2 && tiles >= 8 * (int64_t)gridDim.x) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < QC_STAGGER) {}
+  }
+#endif
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t s_warp = tile * QC_TILE + warp * 4;  // first of this warp's 4 samples
     // ---- inputs: 4 cells for each of the two row tiles (samples 0,1 and 2,3 of the warp) ------------
@@ -183,11 +195,13 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
 
     // ---- fc1: 8 pooled samples x 32 of the 64 hidden units per warp, K = 256; the weights stream from
     // L2 through two register blocks of FC1_BLK k-steps (load block j+1 while block j multiplies) ------
-    double h[4][2];
+    // two accumulator sets (even / odd k-steps): 8 independent DMMA chains per warp instead of 4
+    double h[4][2], g[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       h[nt][0] = b3s[wip * 32 + nt * 8 + 2 * fk];
       h[nt][1] = b3s[wip * 32 + nt * 8 + 2 * fk + 1];
+      g[nt][0] = g[nt][1] = 0.0;
     }
     const double* arow = in2p + fr * IN2_STRIDE + fk;
 #pragma unroll
@@ -203,8 +217,16 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
       for (int ks = 0; ks < FC1_BLK; ++ks) {
         const double a = arow[(blk * FC1_BLK + ks) * 4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma(h[nt][0], h[nt][1], a, wb[blk & 1][ks][nt]);
+        for (int nt = 0; nt < 4; ++nt) {
+          if (ks & 1) dmma(g[nt][0], g[nt][1], a, wb[blk & 1][ks][nt]);
+          else dmma(h[nt][0], h[nt][1], a, wb[blk & 1][ks][nt]);
+        }
       }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      h[nt][0] += g[nt][0];
+      h[nt][1] += g[nt][1];
     }
 
     // ---- output layer: each lane owns 8 hidden units of one sample; 4 partial dot products, summed
