@@ -3,7 +3,8 @@
 Same entry points, argument order and return types as the reference (``src/dqn_lib.py:8-244``), so
 ``double_dqn_conv.py``, ``double_dqn_dense.py`` and ``player.py`` run unchanged:
 
-  epsilon_greedy_policy   legal mask (kernel K1) + fused Q-normalise/mask/argmax (kernel K0)
+  epsilon_greedy_policy   legal mask (kernel K1) + Q forward (conv net: fused kernel K6) + fused
+                          Q-normalise/mask/argmax (kernel K0)
   play_one_step           Board2048.peek_action on the GPU + replay append
   sample_experiences      GPU ring: fused sample + gather + unpack to float64 (kernel K2)
   train_step              Q forwards in torch float64 + fused Double-DQN target / summed MSE (K3)
@@ -21,6 +22,7 @@ from __future__ import annotations
 
 import copy
 import os
+import weakref
 from collections import deque
 from typing import Callable
 
@@ -30,6 +32,7 @@ import torch
 from board import Board2048
 from b2048 import ddqn as _ddqn
 from b2048 import env as _env
+from b2048 import qfused as _qfused
 from b2048.qnet import accelerate as _accelerate
 from b2048.replay import ReplayDeque
 
@@ -64,6 +67,34 @@ def board_as_flattened_tensor(board: Board2048, device: str) -> torch.Tensor:
     return _exponent_tensor([board], (16,), device)
 
 
+_FUSED = weakref.WeakKeyDictionary()        # model -> FusedConvQ (or None when the model is something else)
+
+
+def _fused_for(model):
+    """FusedConvQ for the reference's conv Q-network on a CUDA device (cached per module), else None."""
+    try:
+        return _FUSED[model]
+    except KeyError:
+        fq = _FUSED[model] = _qfused.FusedConvQ(model) if _qfused.matches(model) else None
+        return fq
+    except TypeError:
+        return None
+
+
+def _fusable(x) -> bool:
+    return x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.numel() == 16 * x.shape[0]
+
+
+def _q_values(model, state, fallback=None):
+    """model(state) where the reference never takes a gradient through the call (action selection,
+    src/dqn_lib.py:24-25; Q(s') of the target, :126-128): the conv Q-network runs as the single fused
+    kernel K6, any other model through `fallback` (default: the module itself)."""
+    fq = _fused_for(model)
+    if fq is not None and _fusable(state):
+        return fq(state)
+    return (fallback or model)(state)
+
+
 def epsilon_greedy_policy(board, epsilon, model, device, board_to_tensor_function: Callable = board_as_4d_tensor):
     """-> (action, done, max_q) exactly as src/dqn_lib.py:16-30."""
     available_moves = board.available_moves_as_torch_unit_vector(device=device)
@@ -71,7 +102,7 @@ def epsilon_greedy_policy(board, epsilon, model, device, board_to_tensor_functio
     if np.random.rand() < epsilon:
         return np.random.randint(4), done, torch.zeros(size=(1,), device=device)
     state = board_to_tensor_function(board, device)
-    q_values = model(state)
+    q_values = _q_values(model, state)
     dev = _cuda_device(device)
     q = q_values.detach().reshape(1, 4).to(dev, torch.float64).contiguous()
     legal = (available_moves.to(dev) != 0).to(torch.uint8)
@@ -176,8 +207,9 @@ def train_step(batch_size: int, discount_factor, model, target_model, replay_buf
     on_dev = states.device == dev
     # same parameters; 2x2 convolutions are evaluated as float64 GEMMs (b2048/qnet.py)
     f_model, f_target = _accelerate(model), _accelerate(target_model)
-    q_next_target = f_target(next_states)
-    q_next_online = f_model(next_states) if use_double_dqn else None
+    # Q(s') enters the loss as a constant: no autograd graph needed for it
+    q_next_target = _q_values(target_model, next_states, f_target)
+    q_next_online = _q_values(model, next_states, f_model) if use_double_dqn else None
     q_cur = f_model(states)
     if on_dev and _is_sum_mse(loss_fn) and q_cur.dtype == torch.float64:
         loss, _, _ = _ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones,
