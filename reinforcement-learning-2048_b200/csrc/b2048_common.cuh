@@ -246,12 +246,10 @@ __device__ __forceinline__ void fill_tabs(SmemTabs* t) {
 // (top nibble 14) and the global path adds its 65536 separately.
 constexpr uint32_t ENTRY_RIGHT = 0x40000000u, ENTRY_OVF = 0x80000000u;
 
-// Look the four transformed rows up.  Fast path: all four rows are in the shared-memory part of
-// the table (checked once per board with a packed 16-bit max); otherwise all four go to the
-// global table (rare: a 16384/32768 tile in the last position of a transformed row).
-__device__ __forceinline__ uint32_t lut_at(const uint32_t* base, uint32_t byte_off) {
-  return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(base) + byte_off);
-}
+// Look the four transformed rows up in the full table in global memory (L2-resident, 256 KB).  Used by
+// the small-batch, all-four-actions and cold paths; the streaming kernel has its own shared-memory
+// lookups (env_kernels.cu: stream_board).  `extra`: 65536 for every row equal to 0xEEEE, whose reward
+// does not fit the table's 14-bit field.
 __device__ __forceinline__ void lookup4_global(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut,
                                                uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3,
                                                uint32_t& extra) {
@@ -262,46 +260,15 @@ __device__ __forceinline__ void lookup4_global(uint32_t zl, uint32_t zh, const u
   e3 = __ldg(glut + i3);
   extra = ((i0 == 0xEEEEu) + (i1 == 0xEEEEu) + (i2 == 0xEEEEu) + (i3 == 0xEEEEu)) * 65536u;
 }
-// out-of-line copy for the rare miss of the shared-memory table (keeps the hot loop small)
-static __device__ __noinline__ uint4 lookup4_global_cold(uint32_t zl, uint32_t zh, const uint32_t* __restrict__ glut) {
-  return make_uint4(__ldg(glut + (zl & 0xFFFFu)), __ldg(glut + (zl >> 16)), __ldg(glut + (zh & 0xFFFFu)),
-                    __ldg(glut + (zh >> 16)));
-}
-// 65536 for every transformed row equal to 0xEEEE (its reward does not fit the table's 14 bits)
-__device__ __forceinline__ uint32_t extra_reward_eeee(uint32_t zl, uint32_t zh) {
-  return (((zl & 0xFFFFu) == 0xEEEEu) + ((zl >> 16) == 0xEEEEu) + ((zh & 0xFFFFu) == 0xEEEEu) +
-          ((zh >> 16) == 0xEEEEu)) * 65536u;
-}
-template <bool SMEM>
-__device__ __forceinline__ void lookup4(uint32_t zl, uint32_t zh, const uint32_t* slut,
-                                        const uint32_t* __restrict__ glut, uint32_t& e0, uint32_t& e1,
-                                        uint32_t& e2, uint32_t& e3, uint32_t& extra) {
-  if (SMEM) {
-    const uint32_t mx = __vmaxu2(zl, zh);
-    if (__builtin_expect((mx >= ((uint32_t)LUT_SMEM_ROWS << 16)) | ((mx & 0xFFFFu) >= (uint32_t)LUT_SMEM_ROWS), 0)) {
-      const uint4 e = lookup4_global_cold(zl, zh, glut);
-      e0 = e.x; e1 = e.y; e2 = e.z; e3 = e.w;
-      extra = extra_reward_eeee(zl, zh);
-    } else {
-      e0 = lut_at(slut, (zl * 4u) & 0x3FFFCu);
-      e1 = lut_at(slut, __byte_perm(zl, 0u, 0x4432) * 4u);   // PRMT + shift-add: one ALU op less than SHF + LOP3
-      e2 = lut_at(slut, (zh * 4u) & 0x3FFFCu);
-      e3 = lut_at(slut, __byte_perm(zh, 0u, 0x4432) * 4u);
-      extra = 0;
-    }
-  } else {
-    lookup4_global(zl, zh, glut, e0, e1, e2, e3, extra);
-  }
-}
 
 // Slide + merge one board by one action, and derive the legal mask of the INPUT board in the
 // transformed frame.  Outputs: slid board (no spawn), reward, flags (legal | done | changed |
 // overflow).
 // tabs == nullptr: the per-action constants are computed instead of read from shared memory (cold
 // paths that have no SmemTabs at hand).
-template <bool SMEM, bool LEGAL = true>
+template <bool LEGAL = true>
 __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a, const SmemTabs* tabs,
-                                            const uint32_t* slut, const uint32_t* __restrict__ glut,
+                                            const uint32_t* __restrict__ glut,
                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward,
                                             uint32_t& flags, uint32_t& changed) {
   const ActXform x = tabs ? tabs->act[a] : act_xform((int)a);
@@ -310,7 +277,7 @@ __device__ __forceinline__ void slide_board(uint32_t lo, uint32_t hi, uint32_t a
   zl = delta_swap(zl, x);
   zh = delta_swap(zh, x);
   uint32_t e0, e1, e2, e3, extra;
-  lookup4<SMEM>(zl, zh, slut, glut, e0, e1, e2, e3, extra);
+  lookup4_global(zl, zh, glut, e0, e1, e2, e3, extra);
   uint32_t wl = (e0 & 0xFFFFu) + (e1 << 16);
   uint32_t wh = (e2 & 0xFFFFu) + (e3 << 16);
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);

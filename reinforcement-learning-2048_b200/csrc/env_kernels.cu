@@ -199,8 +199,7 @@ __device__ __noinline__ void fix_quad(uint32_t quad, const uint4* __restrict__ b
                                              (uint32_t)(step >> 32)), keys);
     const uint32_t w = pick_word(r, (uint32_t)g & 3u);
     uint32_t nl, nh, rw, f, ch;
-    slide_board<false>((uint32_t)bd, (uint32_t)(bd >> 32), (a4 >> (8 * j)) & 3u, nullptr, nullptr, glut, nl, nh,
-                       rw, f, ch);
+    slide_board<true>((uint32_t)bd, (uint32_t)(bd >> 32), (a4 >> (8 * j)) & 3u, nullptr, glut, nl, nh, rw, f, ch);
     finish_board<HAS_OVERRIDE>(nl, nh, ch, w, p4, (o4 >> (8 * j)) & 0xFFu, f);
     nq[j] = ((uint64_t)nh << 32) | nl;
     rq[j] = (int32_t)rw;
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(256)
   const uint64_t g = index_base + (uint64_t)i;
   const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
   uint32_t nl, nh, rw, f, ch;
-  slide_board<false>(lo, hi, actions[i] & 3u, &tabs, nullptr, glut, nl, nh, rw, f, ch);
+  slide_board<true>(lo, hi, actions[i] & 3u, &tabs, glut, nl, nh, rw, f, ch);
   finish_board<HAS_OVERRIDE>(nl, nh, ch, w, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
   next[i] = ((uint64_t)nh << 32) | nl;
   reward[i] = (int32_t)rw;
@@ -350,8 +349,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- all four actions per board (BASELINE.json config 2) ------------------------------------------
-template <bool SMEM, bool HAS_OVERRIDE>
-__device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemTabs* tabs, const uint32_t* slut,
+template <bool HAS_OVERRIDE>
+__device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemTabs* tabs,
                                            const uint32_t* __restrict__ glut, uint32_t w,
                                            uint32_t p4, uint32_t ovr4, uint32_t nl[4],
                                            uint32_t nh[4], uint32_t rw[4], uint32_t& flags) {
@@ -359,7 +358,7 @@ __device__ __forceinline__ void all4_board(uint32_t lo, uint32_t hi, const SmemT
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     uint32_t f, ch;
-    slide_board<SMEM, false>(lo, hi, (uint32_t)a, tabs, slut, glut, nl[a], nh[a], rw[a], f, ch);
+    slide_board<false>(lo, hi, (uint32_t)a, tabs, glut, nl[a], nh[a], rw[a], f, ch);
     legal |= ch ? (1u << a) : 0u;    // legal == the move changes the board
     extra |= f & B2048_FLAG_OVERFLOW;
     finish_board<HAS_OVERRIDE>(nl[a], nh[a], ch, w, p4, HAS_OVERRIDE ? ((ovr4 >> (8 * a)) & 0xFFu) : 0xFFu, f);
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(256)
   const uint64_t g = index_base + (uint64_t)i;
   const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
   uint32_t nl[4], nh[4], rw[4], f;
-  all4_board<false, HAS_OVERRIDE>(lo, hi, &tabs, nullptr, glut, w, p4,
+  all4_board<HAS_OVERRIDE>(lo, hi, &tabs, glut, w, p4,
                                   HAS_OVERRIDE ? override4[i] : 0xFFFFFFFFu, nl, nh, rw, f);
   st_stream_v4(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]));
   st_stream_v4(next4 + 2 * i + 1, make_uint4(nl[2], nh[2], nl[3], nh[3]));
