@@ -281,6 +281,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
+        # (NCCL ignores NCCL_DEBUG_FILE at level VERSION, so that level is raised to WARN)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n = BOARDS_PER_GPU
