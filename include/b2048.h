@@ -273,7 +273,8 @@ int egreedy_select(const double* q, const uint8_t* flags, double eps, uint64_t s
  * replay_sample / b2048_unpack_f64 write) is non-NULL.  scaling (boards only): 0 = exponents as
  * board.log_scale() (src/board.py:224-231), 1 = tile / largest tile as board.normalized()
  * (src/board.py:218-222).  Weights are the module's own parameter tensors, contiguous float64:
- * w1[64,1,2,2] b1[64] w2[64,64,2,2] b2[64] w3[64,256] b3[64] w4[4,64] b4[4].  q: float64 [n,4].
+ * w1[64,1,2,2] b1[64] w2[64,64,2,2] (16-byte aligned) b2[64] w3[64,256] b3[64] w4[4,64] b4[4].
+ * q: float64 [n,4].
  * Summation order differs from cuBLAS/cuDNN (agreement ~1e-13 relative). */
 int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scaling, const double* w1,
                           const double* b1, const double* w2, const double* b2, const double* w3,

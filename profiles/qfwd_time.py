@@ -19,7 +19,7 @@ def timeit(f, k=20):
     for _ in range(k): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
-for n in (4096, 65536, 1 << 20):
+for n in (4096, 5000, 65536, 1 << 20):
     b = env.random_boards(n, device=dev)
     x = env.unpack_f64(b, conv=True)
     with torch.no_grad():

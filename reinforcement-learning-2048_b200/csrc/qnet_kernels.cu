@@ -25,7 +25,6 @@ namespace b2048 {
 namespace {
 
 constexpr int QC_THREADS = 256;           // 8 warps = 4 warp pairs
-constexpr int QC_TILE = 32;               // samples per CTA iteration (4 per warp)
 #ifndef QC_STAGGER
 #define QC_STAGGER 20000                  // cycles; 0 disables
 #endif
@@ -71,6 +70,10 @@ __device__ __forceinline__ double cell_value(uint64_t bd, int cell, int scaling,
   return __longlong_as_double((long long)(1023 + e - emax) << 52);   // 2^(e - emax), exact
 }
 
+// MT = conv2 row tiles per warp: 2 (4 boards per warp, 32 per CTA iteration) for long launches, 1 (2 per
+// warp, 16 per iteration; fc1 then runs on half-filled row tiles) when the launch is so short that the
+// finer granularity fills more SMs (n <= 16 * #SMs: one short round instead of one long one).
+template <int MT>
 __global__ void __launch_bounds__(QC_THREADS, 1)
     qconv_forward_kernel(const uint64_t* __restrict__ boards, const double* __restrict__ states, int scaling,
                          const QConvWeights wts, double* __restrict__ q, int64_t n) {
@@ -90,10 +93,15 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   // ---- stage the weights: conv2 in B-fragment order, the small ones as they are --------------------
   // B fragment of mma.m8n8k4 (col): lane holds B[k = lane % 4][n = lane / 4];  k-step = c1, k = tap,
   // n-tile nt covers output channels nt*8 .. nt*8+7:  w2f[(c1*8 + nt)*32 + lane] = W2[nt*8 + lane/4][c1*4 + lane%4]
-  for (int i = tid; i < 64 * 8 * 32; i += QC_THREADS) {
-    const int l = i & 31, nt = (i >> 5) & 7, c1 = i >> 8;
-    w2f[i] = __ldg(wts.w2 + (nt * 8 + (l >> 2)) * 256 + c1 * 4 + (l & 3));
+  // The four taps of one (c1, channel) are 32 contiguous bytes on both sides: 16-byte cp.async copies,
+  // all in flight at once (one L2 round trip instead of 64 dependent ones).
+  for (int i = tid; i < 64 * 8 * 32 / 2; i += QC_THREADS) {
+    const int half = i & 1, ch8 = (i >> 1) & 7, nt = (i >> 4) & 7, c1 = i >> 7;   // unit = 2 doubles
+    const double* src = wts.w2 + (nt * 8 + ch8) * 256 + c1 * 4 + half * 2;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w2f + (c1 * 8 + nt) * 32 + ch8 * 4 + half * 2);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < 64 * 8; i += QC_THREADS) {
     const int c1 = i >> 3, j = i & 7;
     w1b[i] = j < 4 ? __ldg(wts.w1 + c1 * 4 + j) : (j == 4 ? __ldg(wts.b1 + c1) : 0.0);
@@ -104,6 +112,8 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   }
   for (int i = tid; i < 4 * 64; i += QC_THREADS) w4s[i] = __ldg(wts.w4 + i);
   if (tid < 4) b4s[tid] = __ldg(wts.b4 + tid);
+  for (int i = tid; i < 4 * 8 * IN2_STRIDE; i += QC_THREADS) in2[i] = 0.0;   // rows a short tile never writes
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // this thread's conv2 row is (sample, position qp) with tap fk: the conv1 output it needs sits at
@@ -113,7 +123,8 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   double* in2p = in2 + pair * 8 * IN2_STRIDE;
   double* qpartp = qpart + pair * 32;
 
-  const int64_t tiles = (n + QC_TILE - 1) / QC_TILE;
+  constexpr int TILE = 16 * MT;                        // boards per CTA iteration, 2 * MT per warp
+  const int64_t tiles = (n + TILE - 1) / TILE;
 #if QC_STAGGER
   // Each scheduler hosts one warp of pairs 0/1 and one of pairs 2/3.  Left alone they run conv2 (DMMA
   // bound) and epilogue + fc1 (latency bound) in lockstep; starting pairs 2/3 a third of a tile later
@@ -124,11 +135,11 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   }
 #endif
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t s_warp = tile * QC_TILE + warp * 4;  // first of this warp's 4 samples
-    // ---- inputs: 4 cells for each of the two row tiles (samples 0,1 and 2,3 of the warp) ------------
-    double x[2][4];
+    const int64_t s_warp = tile * TILE + warp * (2 * MT);   // first of this warp's boards
+    // ---- inputs: 4 cells for each row tile (2 boards x 4 conv2 positions per tile) -------------------
+    double x[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       const int64_t s = s_warp + mt * 2 + (fr >> 2);
       if (s < n) {
         if (boards) {
@@ -151,26 +162,30 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
       }
     }
 
-    // ---- conv1 (on the fly) + conv2: 16 rows x 64 columns per warp, K = 64 channels x 4 taps --------
+    // ---- conv1 (on the fly) + conv2: 8 * MT rows x 64 columns per warp, K = 64 channels x 4 taps ----
     // accumulators start at the bias: C fragment, lane holds C[row = lane / 4][col = 2 * (lane % 4) + {0,1}]
-    double acc[2][8][2];
+    double acc[MT][8][2];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      acc[0][nt][0] = acc[1][nt][0] = b2s[nt * 8 + 2 * fk];
-      acc[0][nt][1] = acc[1][nt][1] = b2s[nt * 8 + 2 * fk + 1];
-    }
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        acc[mt][nt][0] = b2s[nt * 8 + 2 * fk];
+        acc[mt][nt][1] = b2s[nt * 8 + 2 * fk + 1];
+      }
 #pragma unroll 2
     for (int c1 = 0; c1 < 64; ++c1) {
       const double4 w = *reinterpret_cast<const double4*>(w1b + c1 * 8);
       const double bias = w1b[c1 * 8 + 4];
-      const double a0 = relu(fma(x[0][3], w.w, fma(x[0][2], w.z, fma(x[0][1], w.y, fma(x[0][0], w.x, bias)))));
-      const double a1 = relu(fma(x[1][3], w.w, fma(x[1][2], w.z, fma(x[1][1], w.y, fma(x[1][0], w.x, bias)))));
+      double a[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        a[mt] = relu(fma(x[mt][3], w.w, fma(x[mt][2], w.z, fma(x[mt][1], w.y, fma(x[mt][0], w.x, bias)))));
       const double* bf = w2f + c1 * 256 + lane;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const double b = bf[nt * 32];
-        dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
-        dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b);
       }
     }
     // first block of fc1 weights: issued now so that the L2 latency hides behind the epilogue + barrier
@@ -182,8 +197,8 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
       for (int nt = 0; nt < 4; ++nt) wb[0][ks][nt] = __ldg(brow + nt * 8 * 256 + ks * 4);
     // ---- ReLU, pooled per warp pair in nn.Flatten order (channel * 4 + position) ---------------------
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      double* row = in2p + (wip * 4 + mt * 2 + (fr >> 2)) * IN2_STRIDE + qp;
+    for (int mt = 0; mt < MT; ++mt) {
+      double* row = in2p + (wip * 2 * MT + mt * 2 + (fr >> 2)) * IN2_STRIDE + qp;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int c2 = nt * 8 + 2 * fk;
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
     }
     pair_barrier(pair);
 
-    // ---- fc1: 8 pooled samples x 32 of the 64 hidden units per warp, K = 256; the weights stream from
+    // ---- fc1: the pair's pooled boards (8 row slots) x 32 of the 64 hidden units per warp, K = 256; the weights stream from
     // L2 through two register blocks of FC1_BLK k-steps (load block j+1 while block j multiplies) ------
     // two accumulator sets (even / odd k-steps): 8 independent DMMA chains per warp instead of 4
     double h[4][2], g[4][2];
@@ -248,8 +263,8 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
     if (wip == 1) qpartp[lane] = mine;
     pair_barrier(pair);
     if (wip == 0) {
-      const int64_t s = tile * QC_TILE + pair * 8 + fr;
-      if (s < n) q[4 * s + fk] = mine + qpartp[lane] + b4s[fk];
+      const int64_t s = tile * TILE + pair * (4 * MT) + fr;   // pooled row fr of the pair (4 * MT valid rows)
+      if (fr < 4 * MT && s < n) q[4 * s + fk] = mine + qpartp[lane] + b4s[fk];
     }
     // Reuse across tiles is ordered by the barriers themselves: a warp stores into in2 for tile t+1 only
     // after barrier 2 of tile t, which its partner reaches after its last in2 read; qpart of tile t+1 is
@@ -260,7 +275,9 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
 }  // namespace
 
 cudaError_t qnet_kernels_configure() {
-  return cudaFuncSetAttribute(qconv_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(qconv_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(qconv_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_BYTES);
 }
 
 }  // namespace b2048
@@ -277,11 +294,19 @@ extern "C" int qnet_conv_forward_f64(const uint64_t* boards, const double* state
   if (n < 0 || (n > 0 && (!q || (!boards && !states) || (boards && states))) || scaling < 0 || scaling > 1 ||
       !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4)
     return B2048_EINVAL;
+  if (reinterpret_cast<uintptr_t>(w2) & 15u) return B2048_EINVAL;   // staged with 16-byte cp.async
   if (n == 0) return B2048_OK;
-  const int64_t tiles = (n + QC_TILE - 1) / QC_TILE;
-  const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  // rounds of CTA iterations each variant needs on this device; measured on B200 a 16-board round costs
+  // about 2/3 of a 32-board one (24 vs 36 us: half the conv2 work, the same fc1 / epilogue latency)
+  const int64_t sms = ctx->sm_count;
+  const int64_t t32 = (n + 31) / 32, t16 = (n + 15) / 16;
+  const int64_t r32 = (t32 + sms - 1) / sms, r16 = (t16 + sms - 1) / sms;
   const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
-  qconv_forward_kernel<<<grid, QC_THREADS, QS_BYTES, static_cast<cudaStream_t>(stream)>>>(boards, states, scaling, w,
-                                                                                         q, n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (67 * r16 < 100 * r32) {
+    qconv_forward_kernel<1><<<(int)(t16 < sms ? t16 : sms), QC_THREADS, QS_BYTES, st>>>(boards, states, scaling, w, q, n);
+  } else {
+    qconv_forward_kernel<2><<<(int)(t32 < sms ? t32 : sms), QC_THREADS, QS_BYTES, st>>>(boards, states, scaling, w, q, n);
+  }
   return (int)cudaGetLastError();
 }
