@@ -208,6 +208,16 @@ int ddqn_target_loss(const double* q_next_online, const double* q_next_target, c
                      float gamma_f32, int use_double, double* target, double* q_sa, double* loss,
                      double* grad_q_cur, int64_t B, void* stream);
 
+/* Patch gather / scatter for the conv Q-network's tiny convolutions written as GEMMs
+ * (configs/double_dqn_conv.py:19-28: kernel_size 2, stride 1, no padding).
+ *   conv_patches_f64:      x [n,c,h,w] -> cols [n*oh*ow, c*kh*kw], (c,kh,kw) order like conv.weight
+ *   conv_patches_grad_f64: d cols -> d x (each input element sums the <= kh*kw patches that read
+ *                          it: a gather, deterministic, no atomics) */
+int conv_patches_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
+                     void* stream);
+int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
+                          int kw, void* stream);
+
 /* Fused Adam step on one flat float64 parameter buffer (= optimizer.step() of torch.optim.Adam
  * without weight decay / amsgrad, configs/double_dqn_*.py: Adam(lr=1e-2); src/dqn_lib.py:163).
  *   t = step_counter[0] + 1;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g
@@ -270,31 +280,6 @@ int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scal
                           const double* b1, const double* w2, const double* b2, const double* w3,
                           const double* b3, const double* w4, const double* b4, double* q, int64_t n,
                           void* stream);
-
-/* ---- element-wise halves of the float64 Q-network layers (autograd path of train_step) ------------- */
-
-/* The Conv2d / Linear + ReLU layers of src/configs/double_dqn_conv.py:19-28 and
- * double_dqn_dense.py:7-15 as they run inside train_step (src/dqn_lib.py:146-163): the GEMM is
- * cuBLAS, these are the parts around it.  All matrices are row-major float64, `cols` even, pointers
- * 16-byte aligned.
- * layer_bias_act_f64: y[r][c] = y[r][c] + bias[c], then max(.,0) if relu — in place on the GEMM output.
- * layer_act_grad_bias_f64: g[r][c] = gy[r][c] * (y[r][c] > 0) (relu) or gy[r][c]; dbias[c] = sum_r g[r][c]
- *   in a fixed order (bit-reproducible).  g may alias gy.  scratch: layer_act_grad_scratch_elems(rows,
- *   cols) doubles. */
-int layer_bias_act_f64(double* y, const double* bias, int64_t rows, int cols, int relu, void* stream);
-int64_t layer_act_grad_scratch_elems(int64_t rows, int cols);
-int layer_act_grad_bias_f64(const double* gy, const double* y, double* g, double* dbias, double* scratch,
-                            int64_t rows, int cols, int relu, void* stream);
-
-/* Patch gather / scatter (im2col / col2im) for the conv Q-network's tiny convolutions written as
- * GEMMs (configs/double_dqn_conv.py:19-28: kernel_size 2, stride 1, no padding).  Activations are row
- * matrices [n*h*w, c] (the layout a GEMM over patches produces), so consecutive convolutions need no
- * NCHW round trip.  cols / dcols: [n*oh*ow, c*kh*kw] in the (c, kh, kw) order of
- * conv.weight.reshape(out, -1); the gradient is a gather per input element (deterministic). */
-int conv_patches_rows_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
-                          void* stream);
-int conv_patches_rows_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
-                               int kw, void* stream);
 
 #ifdef __cplusplus
 }

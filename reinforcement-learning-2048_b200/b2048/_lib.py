@@ -52,6 +52,8 @@ SIGNATURES = {
     "ddqn_target_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p]),
+    "conv_patches_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "conv_patches_grad_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ddqn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double,
                                ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
     "p2p_get_ipc_handle": (c_int, [c_void_p, ctypes.c_char_p]),
@@ -61,11 +63,6 @@ SIGNATURES = {
                                        ctypes.c_double, c_void_p]),
     "egreedy_select": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_uint64, c_uint64, c_uint64,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "layer_bias_act_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
-    "layer_act_grad_scratch_elems": (c_int64, [c_int64, c_int]),
-    "layer_act_grad_bias_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
-    "conv_patches_rows_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "conv_patches_rows_grad_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "qnet_conv_forward_f64": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_void_p, c_int64, c_void_p]),
 }
 

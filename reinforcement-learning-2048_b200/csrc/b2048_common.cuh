@@ -42,8 +42,7 @@ enum : uint32_t {
 struct DeviceCtx {
   uint32_t* lut = nullptr;       // [65536] row table + [LUT_SMEM_ROWS] swizzled copy for shared memory
   double* partials = nullptr;    // [MAX_PARTIALS] loss partial sums
-  unsigned int* ticket = nullptr;// last-block-done counter (K3)
-  unsigned int* ticket2 = nullptr;// last-block-done counter (layer_act_grad_bias_f64)
+  unsigned int* ticket = nullptr;// last-block-done counter
   int sm_count = 0;
   int max_smem_optin = 0;
   bool ready = false;

@@ -91,6 +91,54 @@ __global__ void __launch_bounds__(K3_THREADS)
   }
 }
 
+// cols[(b*oh + oy)*ow + ox][(ci*kh + ky)*kw + kx] = x[b][ci][oy+ky][ox+kx].
+// One thread per (patch, channel): it writes kh*kw consecutive doubles; consecutive threads take
+// consecutive channels, so a warp writes one contiguous run.  Index type is 32-bit when it fits.
+template <typename I>
+__global__ void patches_kernel(const double* __restrict__ x, double* __restrict__ cols, I total, int c, int h,
+                               int w, int kh, int kw, int oh, int ow) {
+  const I i = (I)blockIdx.x * blockDim.x + threadIdx.x;   // = patch * c + ci
+  if (i >= total) return;
+  const I patch = i / (I)c;
+  const int ci = (int)(i - patch * (I)c);
+  const int ox = (int)(patch % (I)ow);
+  const I t = patch / (I)ow;
+  const int oy = (int)(t % (I)oh);
+  const I b = t / (I)oh;
+  const double* src = x + ((b * c + ci) * h + oy) * (I)w + ox;
+  double* dst = cols + i * (I)(kh * kw);
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) dst[ky * kw + kx] = src[ky * w + kx];
+}
+
+// dx[b][ci][y][x] = sum over (ky,kx) with 0 <= y-ky < oh, 0 <= x-kx < ow of
+// dcols[patch (y-ky, x-kx)][(ci*kh + ky)*kw + kx]: a gather per input element (deterministic).
+// Thread order (b, y, x, ci) with ci fastest keeps the dcols reads of a warp contiguous-ish.
+template <typename I>
+__global__ void patches_grad_kernel(const double* __restrict__ dcols, double* __restrict__ dx, I total, int c,
+                                    int h, int w, int kh, int kw, int oh, int ow) {
+  const I i = (I)blockIdx.x * blockDim.x + threadIdx.x;   // = ((b*h + y)*w + x)*c + ci
+  if (i >= total) return;
+  const I pix = i / (I)c;
+  const int ci = (int)(i - pix * (I)c);
+  const int xx = (int)(pix % (I)w);
+  const I t = pix / (I)w;
+  const int yy = (int)(t % (I)h);
+  const I b = t / (I)h;
+  const I K = (I)c * kh * kw;
+  double acc = 0.0;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int oy = yy - ky;
+    if (oy < 0 || oy >= oh) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int ox = xx - kx;
+      if (ox < 0 || ox >= ow) continue;
+      acc += dcols[((b * oh + oy) * ow + ox) * K + (I)((ci * kh + ky) * kw + kx)];
+    }
+  }
+  dx[((b * c + ci) * h + yy) * (I)w + xx] = acc;
+}
+
 __global__ void adam_kernel(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,
                             double* __restrict__ v, const int64_t* __restrict__ step, int64_t n, double lr,
                             double b1, double b2, double eps) {
@@ -181,6 +229,42 @@ extern "C" int ddqn_target_loss(const double* q_next_online, const double* q_nex
   ddqn_target_loss_kernel<<<(unsigned)blocks, K3_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       q_next_online, q_next_target, q_cur, actions, rewards, dones, gamma_f32, use_double, target,
       q_sa, loss, grad_q_cur, B, ctx->partials, ctx->ticket);
+  return (int)cudaGetLastError();
+}
+
+static int patches_args_ok(int64_t n, int c, int h, int w, int kh, int kw) {
+  return n > 0 && c > 0 && kh > 0 && kw > 0 && h >= kh && w >= kw;
+}
+
+extern "C" int conv_patches_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
+                                void* stream) {
+  if (!x || !cols || !patches_args_ok(n, c, h, w, kh, kw)) return B2048_EINVAL;
+  int err = 0;
+  if (!current_ctx(&err)) return err;
+  const int oh = h - kh + 1, ow = w - kw + 1;
+  const int64_t total = n * oh * ow * c;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (total * kh * kw < (1ll << 31) && n * c * h * w < (1ll << 31))
+    patches_kernel<uint32_t><<<grid, 256, 0, st>>>(x, cols, (uint32_t)total, c, h, w, kh, kw, oh, ow);
+  else
+    patches_kernel<int64_t><<<grid, 256, 0, st>>>(x, cols, total, c, h, w, kh, kw, oh, ow);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
+                                     int kw, void* stream) {
+  if (!dcols || !dx || !patches_args_ok(n, c, h, w, kh, kw)) return B2048_EINVAL;
+  int err = 0;
+  if (!current_ctx(&err)) return err;
+  const int oh = h - kh + 1, ow = w - kw + 1;
+  const int64_t total = n * c * h * w;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n * oh * ow * c * kh * kw < (1ll << 31) && total < (1ll << 31))
+    patches_grad_kernel<uint32_t><<<grid, 256, 0, st>>>(dcols, dx, (uint32_t)total, c, h, w, kh, kw, oh, ow);
+  else
+    patches_grad_kernel<int64_t><<<grid, 256, 0, st>>>(dcols, dx, total, c, h, w, kh, kw, oh, ow);
   return (int)cudaGetLastError();
 }
 

@@ -132,9 +132,8 @@ extern "C" int b2048_init(int device) {
       cudaSuccess)
     return (int)e;
   if ((e = cudaMalloc(&c->partials, MAX_PARTIALS * sizeof(double))) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&c->ticket, 2 * sizeof(unsigned int))) != cudaSuccess) return (int)e;
-  if ((e = cudaMemset(c->ticket, 0, 2 * sizeof(unsigned int))) != cudaSuccess) return (int)e;
-  c->ticket2 = c->ticket + 1;
+  if ((e = cudaMalloc(&c->ticket, sizeof(unsigned int))) != cudaSuccess) return (int)e;
+  if ((e = cudaMemset(c->ticket, 0, sizeof(unsigned int))) != cudaSuccess) return (int)e;
   if ((e = env_kernels_configure()) != cudaSuccess) return (int)e;
   if ((e = qnet_kernels_configure()) != cudaSuccess) return (int)e;
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;

@@ -241,49 +241,3 @@ def test_full_size_properties(cuda):
         n4 += int((d == 4).sum())
         nchanged += int(changed.sum())
     assert 0.095 < n4 / nchanged < 0.105        # 10 % fours
-
-
-def _mirror(b):
-    """Horizontal flip of packed boards: reverse the four nibbles of every 16-bit row."""
-    b = ((b >> 4) & 0x0F0F0F0F0F0F0F0F) | ((b & 0x0F0F0F0F0F0F0F0F) << 4)
-    return ((b >> 8) & 0x00FF00FF00FF00FF) | ((b & 0x00FF00FF00FF00FF) << 8)
-
-
-def _transpose(b):
-    """Transpose of the 4x4 nibble matrix (two delta swaps)."""
-    t = (b ^ (b >> 12)) & 0x0000F0F00000F0F0
-    b = b ^ t ^ (t << 12)
-    t = (b ^ (b >> 24)) & 0x00000000FF00FF00
-    return b ^ t ^ (t << 24)
-
-
-def test_full_size_symmetries(cuda):
-    """16M boards: the four directions are one slide seen through the symmetries of the square —
-    right = mirror . left . mirror, up = transpose . left . transpose, down = transpose . right .
-    transpose — for boards, rewards and the CHANGED bit, with the legal mask permuted accordingly
-    (spawns skipped).  Checks the per-action transform constants of the kernel at scale."""
-    n = 1 << 24
-    b = env.random_boards(n, seed=99, p_empty=0.35, max_exp=13, device=cuda)
-    assert torch.equal(_mirror(_mirror(b)), b) and torch.equal(_transpose(_transpose(b)), b)
-    skip = torch.full((n,), env.SPAWN_SKIP, dtype=torch.uint8, device=cuda)
-
-    def move(boards, a):
-        return env.step(boards, torch.full((n,), a, dtype=torch.uint8, device=cuda), spawn_override=skip)
-
-    def perm_legal(f, perm):          # perm[j] = bit of the transformed board that is bit j of the original
-        f = f.to(torch.int64)
-        out = torch.zeros_like(f)
-        for j, p in enumerate(perm):
-            out |= ((f >> p) & 1) << j
-        return out | (f & 0x70)       # DONE / CHANGED / OVERFLOW are symmetric
-
-    UP, DOWN, LEFT, RIGHT = 0, 1, 2, 3
-    l_next, l_rew, l_flg = move(b, LEFT)
-    m_next, m_rew, m_flg = move(_mirror(b), RIGHT)           # mirror swaps left <-> right
-    assert torch.equal(_mirror(m_next), l_next) and torch.equal(m_rew, l_rew)
-    assert torch.equal(perm_legal(m_flg, [UP, DOWN, RIGHT, LEFT]), l_flg.to(torch.int64))
-    t_next, t_rew, t_flg = move(_transpose(b), UP)           # transpose swaps up <-> left, down <-> right
-    assert torch.equal(_transpose(t_next), l_next) and torch.equal(t_rew, l_rew)
-    assert torch.equal(perm_legal(t_flg, [LEFT, RIGHT, UP, DOWN]), l_flg.to(torch.int64))
-    d_next, d_rew, d_flg = move(_transpose(_mirror(b)), DOWN)  # left on b == down on transpose(mirror(b))
-    assert torch.equal(_mirror(_transpose(d_next)), l_next) and torch.equal(d_rew, l_rew)
