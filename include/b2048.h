@@ -281,6 +281,18 @@ int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scal
                           const double* b3, const double* w4, const double* b4, double* q, int64_t n,
                           void* stream);
 
+/* ---- weight + bias gradient of a layer with a tiny weight matrix ----------------------------------- */
+
+/* In train_step's backward (src/dqn_lib.py:159-161): dW[c][k] = sum_r g[r][c] * x[r][k] and
+ * db[c] = sum_r g[r][c] for the first convolution (as a GEMM over patches, weight 64 x 4) and the
+ * output layer (Linear(64,4)) of src/configs/double_dqn_conv.py:19-28 — a tall-skinny reduction over
+ * 45 000 / 5 000 rows that cuBLAS + ATen run on one or two CTAs.  g [rows,C], x [rows,K] row-major
+ * float64, C, K <= 64, C*K <= 1024; dw [C,K], db [C]; fixed summation order (bit-reproducible).
+ * scratch: layer_wgrad_small_scratch_elems(rows, C, K) doubles. */
+int64_t layer_wgrad_small_scratch_elems(int64_t rows, int C, int K);
+int layer_wgrad_small_f64(const double* g, const double* x, double* dw, double* db, double* scratch,
+                          int64_t rows, int C, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,8 @@ SIGNATURES = {
                                        ctypes.c_double, c_void_p]),
     "egreedy_select": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_uint64, c_uint64, c_uint64,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "layer_wgrad_small_scratch_elems": (c_int64, [c_int64, c_int, c_int]),
+    "layer_wgrad_small_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "qnet_conv_forward_f64": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_void_p, c_int64, c_void_p]),
 }
 

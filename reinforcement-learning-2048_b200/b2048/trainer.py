@@ -40,6 +40,7 @@ class DDQNUpdater:
         self.grads = bdist.FlatGrads(model, tail=2 * world if use_p2p else 0)   # one allreduce, one fused Adam kernel
         self.opt = ddqn.FusedAdam(self.params.flat, self.grads.flat, lr=lr)
         self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.side2 = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         # gradient exchange: "p2p" = fused NVLink allreduce+Adam kernel, "nccl" = all_reduce then Adam
         self.exchange = None
         if use_p2p:
@@ -64,15 +65,21 @@ class DDQNUpdater:
     def _update_eager(self):
         states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
                                                                         out=self.batch)
-        # the two no-grad forwards run on a side stream next to the autograd forward (the kernels
+        # the two no-grad forwards run on side streams next to the autograd forward (the kernels
         # are small; the fork/join is captured into the CUDA graph)
         main = torch.cuda.current_stream(self.device)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side), torch.no_grad():
             q_next_target = self._infer(self.i_target, next_states)
-            q_next_online = self._infer(self.i_model, next_states) if self.use_double else None
+        q_next_online = None
+        if self.use_double:      # its own stream: a short K6 launch leaves most SMs free after its first round
+            self.side2.wait_stream(main)
+            with torch.cuda.stream(self.side2), torch.no_grad():
+                q_next_online = self._infer(self.i_model, next_states)
         q_cur = self.f_model(self._shape(states))
         main.wait_stream(self.side)
+        if self.use_double:
+            main.wait_stream(self.side2)
         if not torch.cuda.is_current_stream_capturing():      # eager mode: tell the allocator about the hand-over
             q_next_target.record_stream(main)
             if q_next_online is not None:

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "b2048.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:const\s+)?(?:int|char\s*\*|const char\*)\s+\**(\w+)\s*\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:const\s+)?(?:int64_t|int|char\s*\*|const char\*)\s+\**(\w+)\s*\(", text, flags=re.M)))
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -153,6 +153,37 @@ def test_fast_conv_forward_equals_cudnn_path(cuda):
         np.testing.assert_allclose(p.grad.cpu().numpy(), u.cpu().numpy(), rtol=1e-10, atol=1e-10 * float(u.abs().max()))
 
 
+@pytest.mark.parametrize("rows,c,k", [(45000, 64, 4), (5000, 4, 64), (1, 2, 3), (127, 16, 64), (128, 64, 16), (40001, 1, 1)])
+def test_small_weight_gradient_kernel(cuda, rows, c, k):
+    """layer_wgrad_small_f64: dW = g^T x and db = column sums of g against torch (1e-12 relative to the
+    largest entry), bit-identical across runs, and argument checks."""
+    from b2048 import _lib
+    from b2048.env import _ptr, _stream
+    _lib.init(torch.device(cuda).index or 0)
+    L = _lib.lib()
+    torch.manual_seed(rows)
+    g = torch.randn(rows, c, dtype=torch.float64, device=cuda)
+    x = torch.randn(rows, k, dtype=torch.float64, device=cuda)
+    scratch = torch.empty(L.layer_wgrad_small_scratch_elems(rows, c, k), dtype=torch.float64, device=cuda)
+
+    def run():
+        dw = torch.full((c, k), float("nan"), dtype=torch.float64, device=cuda)
+        db = torch.full((c,), float("nan"), dtype=torch.float64, device=cuda)
+        with torch.cuda.device(cuda):
+            assert L.layer_wgrad_small_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), rows, c, k, _stream(g)) == 0
+        return dw, db
+
+    dw, db = run()
+    dw2, db2 = run()
+    want_w, want_b = g.t() @ x, g.sum(0)
+    assert float((dw - want_w).abs().max()) <= 1e-12 * max(1.0, float(want_w.abs().max()))
+    assert float((db - want_b).abs().max()) <= 1e-12 * max(1.0, float(want_b.abs().max()))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    with torch.cuda.device(cuda):
+        assert L.layer_wgrad_small_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), rows, 65, k, _stream(g)) == -2
+        assert L.layer_wgrad_small_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), None, rows, c, k, _stream(g)) == -2
+
+
 def test_batched_player_baselines(cuda):
     """The reference's player.py policies at scale: random-legal and up-left baselines."""
     from b2048.player import BatchedPlayer
