@@ -293,6 +293,16 @@ int64_t layer_wgrad_small_scratch_elems(int64_t rows, int C, int K);
 int layer_wgrad_small_f64(const double* g, const double* x, double* dw, double* db, double* scratch,
                           int64_t rows, int C, int K, void* stream);
 
+/* The same gradients for a layer with 64 outputs and K = 32, 64, ... 256 inputs (the second convolution
+ * as a GEMM over patches, 20 000 rows, and Linear(256,64), 5 000 rows, of the conv Q-network) on the
+ * FP64 tensor cores: the rows are split over the SMs, every CTA multiplies its range with DMMA from
+ * cp.async-staged shared-memory tiles, the per-CTA results are added in a fixed order.  g [rows,64],
+ * x [rows,K] row-major float64, 16-byte aligned; dw [64,K], db [64].
+ * scratch: layer_wgrad64_scratch_elems(rows, K) doubles, 16-byte aligned. */
+int64_t layer_wgrad64_scratch_elems(int64_t rows, int K);
+int layer_wgrad64_f64(const double* g, const double* x, double* dw, double* db, double* scratch, int64_t rows,
+                      int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

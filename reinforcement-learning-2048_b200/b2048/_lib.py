@@ -65,6 +65,8 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "layer_wgrad_small_scratch_elems": (c_int64, [c_int64, c_int, c_int]),
     "layer_wgrad_small_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "layer_wgrad64_scratch_elems": (c_int64, [c_int64, c_int]),
+    "layer_wgrad64_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "qnet_conv_forward_f64": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_void_p, c_int64, c_void_p]),
 }
 

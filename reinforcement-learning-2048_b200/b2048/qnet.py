@@ -47,12 +47,22 @@ class _Patches(torch.autograd.Function):
         return dx, None, None
 
 
-class _AddmmSmallWeight(torch.autograd.Function):
-    """y = x @ W^T + b for a layer whose weight matrix is tiny (<= 64 x 64, <= 1024 entries): the forward
-    is cuBLAS addmm; the backward computes dW and db with `layer_wgrad_small_f64` — one pass over the
-    rows spread over the whole GPU with a fixed summation order — instead of a tall-skinny cuBLAS DGEMM
-    on one or two CTAs plus ATen's column reduction (conv1 of the reference's conv net: 57 + 21 us ->
-    a few us inside the update graph)."""
+def _wgrad_kind(c: int, k: int):
+    """Which hand-written weight-gradient kernel covers a [c, k] weight matrix, if any."""
+    if c <= 64 and k <= 64 and c * k <= 1024:
+        return "small"                       # layer_wgrad_small_f64 (conv1 64x4, output layer 4x64)
+    if c == 64 and k % 32 == 0 and k <= 256:
+        return "dmma64"                      # layer_wgrad64_f64 (conv2 and fc1 of the conv net: 64x256)
+    return None
+
+
+class _AddmmOwnWgrad(torch.autograd.Function):
+    """y = x @ W^T + b with the forward on cuBLAS (addmm) and dW, db from the hand-written kernels in
+    csrc/wgrad_kernels.cu.  These gradients are reductions over the 5 000 .. 45 000 rows of the batch
+    into a tiny matrix; cuBLAS runs them as a tall-skinny DGEMM on a handful of CTAs and ATen adds a
+    generic column reduction for the bias (conv net, inside the update graph: 57+21, 50+14, 22+10 and
+    8+7 us for the four layers).  The kernels split the rows over all SMs and add the per-CTA partial
+    results in a fixed order, so the update stays bit-reproducible."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -67,25 +77,27 @@ class _AddmmSmallWeight(torch.autograd.Function):
         gy = gy.contiguous()
         rows, c = gy.shape
         k = x.shape[1]
+        L = _lib.lib()
         gw = torch.empty((c, k), dtype=gy.dtype, device=gy.device)
         gb = torch.empty(c, dtype=gy.dtype, device=gy.device)
-        scratch = torch.empty(_lib.lib().layer_wgrad_small_scratch_elems(rows, c, k), dtype=gy.dtype, device=gy.device)
         with torch.cuda.device(gy.device):
-            _lib.check(_lib.lib().layer_wgrad_small_f64(_ptr(gy), _ptr(x), _ptr(gw), _ptr(gb), _ptr(scratch), rows, c, k,
-                                                        _stream(gy)), "layer_wgrad_small_f64")
+            if _wgrad_kind(c, k) == "small":
+                scratch = torch.empty(L.layer_wgrad_small_scratch_elems(rows, c, k), dtype=gy.dtype, device=gy.device)
+                _lib.check(L.layer_wgrad_small_f64(_ptr(gy), _ptr(x), _ptr(gw), _ptr(gb), _ptr(scratch), rows, c, k,
+                                                   _stream(gy)), "layer_wgrad_small_f64")
+            else:
+                scratch = torch.empty(L.layer_wgrad64_scratch_elems(rows, k), dtype=gy.dtype, device=gy.device)
+                _lib.check(L.layer_wgrad64_f64(_ptr(gy), _ptr(x), _ptr(gw), _ptr(gb), _ptr(scratch), rows, k,
+                                               _stream(gy)), "layer_wgrad64_f64")
         gx = torch.mm(gy, weight) if ctx.needs_input_grad[0] else None
         return gx, gw, gb
 
 
-def _small_weight(x: torch.Tensor, weight2d: torch.Tensor) -> bool:
-    c, k = weight2d.shape
-    return (x.is_cuda and x.dtype == torch.float64 and x.dim() == 2 and c <= 64 and k <= 64 and c * k <= 1024
-            and torch.is_grad_enabled() and weight2d.requires_grad)
-
-
 def _affine(x: torch.Tensor, weight2d: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    if _small_weight(x, weight2d):
-        return _AddmmSmallWeight.apply(x.contiguous(), weight2d, bias)
+    own = (x.is_cuda and x.dtype == torch.float64 and x.dim() == 2 and torch.is_grad_enabled()
+           and weight2d.requires_grad and _wgrad_kind(*weight2d.shape) is not None)
+    if own:
+        return _AddmmOwnWgrad.apply(x.contiguous(), weight2d, bias)
     return torch.addmm(bias, x, weight2d.t())
 
 

@@ -9,6 +9,7 @@ namespace b2048 {
 
 cudaError_t env_kernels_configure();
 cudaError_t qnet_kernels_configure();
+cudaError_t wgrad_kernels_configure();
 int step_device(DeviceCtx* ctx, const uint64_t* boards, const uint8_t* actions, uint64_t* next,
                 int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed, uint64_t step,
                 uint64_t index_base, uint32_t p4, const uint8_t* ovr, cudaStream_t st);
@@ -136,6 +137,7 @@ extern "C" int b2048_init(int device) {
   if ((e = cudaMemset(c->ticket, 0, sizeof(unsigned int))) != cudaSuccess) return (int)e;
   if ((e = env_kernels_configure()) != cudaSuccess) return (int)e;
   if ((e = qnet_kernels_configure()) != cudaSuccess) return (int)e;
+  if ((e = wgrad_kernels_configure()) != cudaSuccess) return (int)e;
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
   c->ready = true;
   cudaSetDevice(prev);

@@ -109,6 +109,115 @@ int64_t wg_blocks(int64_t rows, int sms) {
   return b < 1 ? 1 : b;
 }
 
+// ---- 64 x K weight gradient on the FP64 tensor cores (conv2 and fc1 of the conv Q-network) -----------
+// dW[64][K] = g^T x over `rows` rows with K = 32 * (warps in use) <= 256: a split over rows.  Every CTA
+// multiplies its row range with DMMA.8x8x4 (M = the 64 output channels, N = K, reduction = rows): warp w
+// owns columns [32w, 32w+32) = 8 x 4 accumulator tiles, 12 shared-memory fragment loads per 32 DMMAs.
+// Row tiles of 32 arrive by cp.async into a double buffer (row strides 68 / 260 doubles: 64-bit fragment
+// loads of a half-warp then hit 16 different banks).  The bias gradient (column sums of g) rides along
+// on 64 threads.  Per-CTA results go to `partials`; wgrad_reduce_kernel adds them in a fixed order.
+constexpr int WT_ROWS = 32;
+constexpr int WT_GS = 68;                               // doubles per g row in shared memory
+constexpr int WT_XS = 260;                              // doubles per x row in shared memory
+constexpr int WT_BUF = WT_ROWS * (WT_GS + WT_XS);       // doubles per buffer
+constexpr int WT_SMEM_BYTES = 2 * WT_BUF * 8;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+    wgrad_dmma_kernel(const double* __restrict__ g, const double* __restrict__ x, double* __restrict__ partials,
+                      int64_t rows, int K, int64_t rows_per_block) {
+  extern __shared__ __align__(16) double wsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+  const int O = 64 * K;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  const bool active = warp * 32 < K;
+
+  auto stage = [&](int buf, int64_t t0) {     // rows [t0, t0+32) -> buffer `buf`; rows past r1 become zeros
+    double* gs = wsm + buf * WT_BUF;
+    double* xs = gs + WT_ROWS * WT_GS;
+    for (int i = tid; i < WT_ROWS * 32; i += 256) {          // g: 32 chunks of 2 doubles per row
+      const int r = i >> 5, c2 = (i & 31) * 2;
+      if (t0 + r < r1) cp_async16(gs + r * WT_GS + c2, g + (t0 + r) * 64 + c2);
+      else gs[r * WT_GS + c2] = gs[r * WT_GS + c2 + 1] = 0.0;
+    }
+    const int xc = K / 2;                                      // chunks per x row
+    for (int i = tid; i < WT_ROWS * xc; i += 256) {
+      const int r = i / xc, c2 = (i - r * xc) * 2;
+      if (t0 + r < r1) cp_async16(xs + r * WT_XS + c2, x + (t0 + r) * K + c2);
+      else xs[r * WT_XS + c2] = xs[r * WT_XS + c2 + 1] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  double accb = 0.0;
+
+  int buf = 0;
+  if (r0 < r1) stage(0, r0);
+  for (int64_t t0 = r0; t0 < r1; t0 += WT_ROWS) {
+    if (t0 + WT_ROWS < r1) {
+      stage(buf ^ 1, t0 + WT_ROWS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double* gs = wsm + buf * WT_BUF;
+    const double* xs = gs + WT_ROWS * WT_GS;
+    if (active) {
+#pragma unroll 2
+      for (int ks = 0; ks < WT_ROWS / 4; ++ks) {
+        // A[m = channel][k = row] = g[row][channel];  B[k = row][n = column] = x[row][column]
+        const double* ga = gs + (ks * 4 + fk) * WT_GS + fr;
+        const double* xb = xs + (ks * 4 + fk) * WT_XS + warp * 32 + fr;
+        double b[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[nt] = xb[nt * 8];
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+          const double a = ga[mt * 8];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                         : "d"(a), "d"(b[nt]));
+        }
+      }
+    }
+    if (tid < 64) {
+#pragma unroll 8
+      for (int r = 0; r < WT_ROWS; ++r) accb += gs[r * WT_GS + tid];
+    }
+    __syncthreads();          // everyone is done with `buf` before the next iteration refills it
+    buf ^= 1;
+  }
+  double* mine = partials + (int64_t)blockIdx.x * (O + 64);
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)   // C fragment: row = fr, columns 2*fk, 2*fk+1 of the tile
+        *reinterpret_cast<double2*>(mine + (mt * 8 + fr) * K + warp * 32 + nt * 8 + 2 * fk) =
+            make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+  }
+  if (tid < 64) mine[O + tid] = accb;
+}
+
+int64_t wt_blocks(int64_t rows, int sms) {
+  int64_t b = (rows + WT_ROWS - 1) / WT_ROWS;
+  if (b > sms) b = sms;
+  return b < 1 ? 1 : b;
+}
+
 }  // namespace
 }  // namespace b2048
 
@@ -140,3 +249,34 @@ extern "C" int layer_wgrad_small_f64(const double* g, const double* x, double* d
   wgrad_reduce_kernel<<<(O + C + 31) / 32, 256, 0, st>>>(scratch, dw, db, O, C, (int)blocks);
   return (int)cudaGetLastError();
 }
+
+extern "C" int64_t layer_wgrad64_scratch_elems(int64_t rows, int K) {
+  (void)rows;
+  return 160 * (64 * (int64_t)K + 64);
+}
+
+extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, double* db, double* scratch,
+                                 int64_t rows, int K, void* stream) {
+  if (rows <= 0 || K <= 0 || K > 256 || (K & 31) || !g || !x || !dw || !db || !scratch ||
+      ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(scratch)) & 15u))
+    return B2048_EINVAL;
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  if (ctx->sm_count > 160) return B2048_EINVAL;
+  const int64_t blocks = wt_blocks(rows, ctx->sm_count);
+  int64_t rpb = (rows + blocks - 1) / blocks;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K, rpb);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const int O = 64 * K;
+  wgrad_reduce_kernel<<<(O + 64 + 31) / 32, 256, 0, st>>>(scratch, dw, db, O, 64, (int)blocks);
+  return (int)cudaGetLastError();
+}
+
+namespace b2048 {
+cudaError_t wgrad_kernels_configure() {
+  return cudaFuncSetAttribute(wgrad_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES);
+}
+}  // namespace b2048

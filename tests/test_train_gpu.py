@@ -184,6 +184,36 @@ def test_small_weight_gradient_kernel(cuda, rows, c, k):
         assert L.layer_wgrad_small_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), None, rows, c, k, _stream(g)) == -2
 
 
+@pytest.mark.parametrize("rows,k", [(20000, 256), (5000, 256), (1, 32), (33, 64), (4737, 128), (63, 256)])
+def test_dmma_weight_gradient_kernel(cuda, rows, k):
+    """layer_wgrad64_f64 (64 x K weight gradient on the FP64 tensor cores) against torch, run to run
+    bit-identical, ragged row counts (partial tiles, fewer row tiles than SMs)."""
+    from b2048 import _lib
+    from b2048.env import _ptr, _stream
+    _lib.init(torch.device(cuda).index or 0)
+    L = _lib.lib()
+    torch.manual_seed(rows + k)
+    g = torch.randn(rows, 64, dtype=torch.float64, device=cuda)
+    x = torch.randn(rows, k, dtype=torch.float64, device=cuda)
+    scratch = torch.empty(L.layer_wgrad64_scratch_elems(rows, k), dtype=torch.float64, device=cuda)
+
+    def run():
+        dw = torch.full((64, k), float("nan"), dtype=torch.float64, device=cuda)
+        db = torch.full((64,), float("nan"), dtype=torch.float64, device=cuda)
+        with torch.cuda.device(cuda):
+            assert L.layer_wgrad64_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), rows, k, _stream(g)) == 0
+        return dw, db
+
+    dw, db = run()
+    dw2, db2 = run()
+    want_w, want_b = g.t() @ x, g.sum(0)
+    assert float((dw - want_w).abs().max()) <= 1e-12 * max(1.0, float(want_w.abs().max()))
+    assert float((db - want_b).abs().max()) <= 1e-12 * max(1.0, float(want_b.abs().max()))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    with torch.cuda.device(cuda):
+        assert L.layer_wgrad64_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), rows, 48, _stream(g)) == -2
+
+
 def test_batched_player_baselines(cuda):
     """The reference's player.py policies at scale: random-legal and up-left baselines."""
     from b2048.player import BatchedPlayer
