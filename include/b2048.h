@@ -208,11 +208,13 @@ int ddqn_target_loss(const double* q_next_online, const double* q_next_target, c
                      float gamma_f32, int use_double, double* target, double* q_sa, double* loss,
                      double* grad_q_cur, int64_t B, void* stream);
 
-/* Patch gather / scatter for the conv Q-network's tiny convolutions written as GEMMs
- * (configs/double_dqn_conv.py:19-28: kernel_size 2, stride 1, no padding).
- *   conv_patches_f64:      x [n,c,h,w] -> cols [n*oh*ow, c*kh*kw], (c,kh,kw) order like conv.weight
- *   conv_patches_grad_f64: d cols -> d x (each input element sums the <= kh*kw patches that read
- *                          it: a gather, deterministic, no atomics) */
+/* Patch gather / scatter (im2col / col2im) for the conv Q-network's tiny convolutions written as GEMMs
+ * (configs/double_dqn_conv.py:19-28: kernel_size 2, stride 1, no padding).  Activations are row
+ * matrices [n*h*w, c] — what a GEMM over patches produces, and for c = 1 the same bytes as NCHW — so
+ * consecutive convolutions need no layout round trip.
+ *   conv_patches_f64:      x [n*h*w, c] -> cols [n*oh*ow, c*kh*kw], (c,kh,kw) order like conv.weight
+ *   conv_patches_grad_f64: d cols -> d x [n*h*w, c] (each input element sums the <= kh*kw patches
+ *                          that read it: a gather, deterministic, no atomics) */
 int conv_patches_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
                      void* stream);
 int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,

@@ -16,17 +16,17 @@ from torch import nn
 
 
 class _Patches(torch.autograd.Function):
-    """x [n,c,h,w] -> cols [n*oh*ow, c*kh*kw] with one gather kernel each way (conv_patches_f64 /
-    conv_patches_grad_f64).  torch's x.unfold(...).unfold(...) backward costs two scatter kernels
-    plus fills (~90 us per update for the second conv), F.unfold is ~100x slower in float64."""
+    """x [n*h*w, c] (activation as a row matrix) -> cols [n*oh*ow, c*kh*kw] with one gather kernel each
+    way (conv_patches_f64 / conv_patches_grad_f64).  torch's x.unfold(...).unfold(...) backward costs two
+    scatter kernels plus fills (~90 us per update for the second conv), F.unfold is ~100x slower in
+    float64."""
 
     @staticmethod
-    def forward(ctx, x, kh, kw):
+    def forward(ctx, x, n, c, h, w, kh, kw):
         from . import _lib
         from .env import _ptr, _stream
         x = x.contiguous()
-        n, c, h, w = x.shape
-        ctx.shape, ctx.k = (n, c, h, w), (kh, kw)
+        ctx.geom = (n, c, h, w, kh, kw)
         cols = torch.empty((n * (h - kh + 1) * (w - kw + 1), c * kh * kw), dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().conv_patches_f64(_ptr(x), _ptr(cols), n, c, h, w, kh, kw, _stream(x)),
@@ -37,14 +37,13 @@ class _Patches(torch.autograd.Function):
     def backward(ctx, dcols):
         from . import _lib
         from .env import _ptr, _stream
-        n, c, h, w = ctx.shape
-        kh, kw = ctx.k
+        n, c, h, w, kh, kw = ctx.geom
         dcols = dcols.contiguous()
-        dx = torch.empty((n, c, h, w), dtype=dcols.dtype, device=dcols.device)
+        dx = torch.empty((n * h * w, c), dtype=dcols.dtype, device=dcols.device)
         with torch.cuda.device(dcols.device):
             _lib.check(_lib.lib().conv_patches_grad_f64(_ptr(dcols), _ptr(dx), n, c, h, w, kh, kw, _stream(dcols)),
                        "conv_patches_grad_f64")
-        return dx, None, None
+        return dx, None, None, None, None, None, None
 
 
 def _wgrad_kind(c: int, k: int):
@@ -101,46 +100,58 @@ def _affine(x: torch.Tensor, weight2d: torch.Tensor, bias: torch.Tensor) -> torc
     return torch.addmm(bias, x, weight2d.t())
 
 
-def _conv_as_gemm(x: torch.Tensor, conv: nn.Conv2d) -> torch.Tensor:
-    n, c, h, w = x.shape
-    kh, kw = conv.kernel_size
-    oh, ow = h - kh + 1, w - kw + 1
-    # patches [n*oh*ow, c*kh*kw] in the (c, kh, kw) order of conv.weight
-    if x.is_cuda and x.dtype == torch.float64:
-        p = _Patches.apply(x, kh, kw)
-    else:
-        p = x.unfold(2, kh, 1).unfold(3, kw, 1).permute(0, 2, 3, 1, 4, 5).reshape(n * oh * ow, c * kh * kw)
-    y = _affine(p, conv.weight.reshape(conv.out_channels, -1), conv.bias)
-    return y.reshape(n, oh, ow, conv.out_channels).permute(0, 3, 1, 2)
-
-
 def _plain_conv(m: nn.Conv2d) -> bool:
     return (m.stride == (1, 1) and m.padding == (0, 0) and m.dilation == (1, 1) and m.groups == 1
             and m.bias is not None and m.padding_mode == "zeros")
 
 
 class FastQNet(nn.Module):
-    """Wraps an nn.Sequential Q-network; Conv2d layers run as float64 GEMMs, the rest as is."""
+    """Wraps the reference's conv Q-network (an nn.Sequential of Conv2d / ReLU / Flatten / Linear on a
+    float64 CUDA device).  Activations live as row matrices [n*h*w, c]: every Conv2d is a patch gather
+    + `_affine` (cuBLAS addmm forward, own weight-gradient kernels backward), nn.Flatten restores the
+    (c, h, w) feature order the Linear weights expect, ReLU is torch's.  The parameters are the wrapped
+    module's own tensors."""
 
     def __init__(self, net: nn.Sequential):
         super().__init__()
         self.net = net
 
+    @staticmethod
+    def supports(net: nn.Module) -> bool:
+        if not isinstance(net, nn.Sequential) or not any(isinstance(m, nn.Conv2d) for m in net):
+            return False
+        for m in net:
+            if isinstance(m, nn.Conv2d):
+                if not _plain_conv(m):
+                    return False
+            elif isinstance(m, nn.Linear):
+                if m.bias is None:
+                    return False
+            elif not isinstance(m, (nn.ReLU, nn.Flatten)):
+                return False
+        return all(p.is_cuda and p.dtype == torch.float64 for p in net.parameters())
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, c, h, w = x.shape
+        rows = (x if c == 1 else x.permute(0, 2, 3, 1)).reshape(n * h * w, c)
         for m in self.net:
-            if isinstance(m, nn.Conv2d) and _plain_conv(m):
-                x = _conv_as_gemm(x, m)
-            elif isinstance(m, nn.Flatten):
-                x = x.reshape(x.shape[0], -1)       # (c, h, w) order like nn.Flatten on NCHW
-            elif isinstance(m, nn.Linear) and m.bias is not None and x.dim() == 2:
-                x = _affine(x, m.weight, m.bias)
+            if isinstance(m, nn.Conv2d):
+                kh, kw = m.kernel_size
+                rows = _affine(_Patches.apply(rows, n, c, h, w, kh, kw), m.weight.reshape(m.out_channels, -1), m.bias)
+                c, h, w = m.out_channels, h - kh + 1, w - kw + 1
+            elif isinstance(m, nn.Linear):
+                rows = _affine(rows.reshape(n, -1), m.weight, m.bias)
+                c, h, w = m.out_features, 1, 1
+            elif isinstance(m, nn.Flatten):                # nn.Flatten on NCHW: feature index (c, h, w)
+                if h * w > 1:
+                    rows = rows.reshape(n, h * w, c).transpose(1, 2).reshape(n, c * h * w)
+                c, h, w = c * h * w, 1, 1
             else:
-                x = m(x)
-        return x
+                rows = torch.relu(rows)
+        return rows.reshape(n, -1) if h * w == 1 else rows.reshape(n, h, w, c).permute(0, 3, 1, 2)
 
 
 def accelerate(net: nn.Module) -> nn.Module:
-    """FastQNet for Sequentials that contain plain small convolutions, otherwise the module itself."""
-    if isinstance(net, nn.Sequential) and any(isinstance(m, nn.Conv2d) and _plain_conv(m) for m in net):
-        return FastQNet(net)
-    return net
+    """FastQNet for float64 CUDA Sequentials of plain small convolutions + ReLU / Flatten / Linear (the
+    reference's conv config), otherwise the module itself."""
+    return FastQNet(net) if FastQNet.supports(net) else net

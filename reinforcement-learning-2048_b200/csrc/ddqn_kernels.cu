@@ -91,9 +91,12 @@ __global__ void __launch_bounds__(K3_THREADS)
   }
 }
 
-// cols[(b*oh + oy)*ow + ox][(ci*kh + ky)*kw + kx] = x[b][ci][oy+ky][ox+kx].
+// Activations are row matrices [b*h*w, c] (what a GEMM over patches produces; for c = 1 the same bytes as
+// NCHW), so consecutive convolutions need no layout round trip.
+// cols[(b*oh + oy)*ow + ox][(ci*kh + ky)*kw + kx] = x[(b*h + oy+ky)*w + ox+kx][ci] — the (c, kh, kw)
+// column order of conv.weight.reshape(out, -1).
 // One thread per (patch, channel): it writes kh*kw consecutive doubles; consecutive threads take
-// consecutive channels, so a warp writes one contiguous run.  Index type is 32-bit when it fits.
+// consecutive channels, so a warp reads and writes contiguous runs.  Index type is 32-bit when it fits.
 template <typename I>
 __global__ void patches_kernel(const double* __restrict__ x, double* __restrict__ cols, I total, int c, int h,
                                int w, int kh, int kw, int oh, int ow) {
@@ -105,15 +108,14 @@ __global__ void patches_kernel(const double* __restrict__ x, double* __restrict_
   const I t = patch / (I)ow;
   const int oy = (int)(t % (I)oh);
   const I b = t / (I)oh;
-  const double* src = x + ((b * c + ci) * h + oy) * (I)w + ox;
+  const double* src = x + (((b * h + oy) * (I)w + ox) * (I)c + ci);
   double* dst = cols + i * (I)(kh * kw);
   for (int ky = 0; ky < kh; ++ky)
-    for (int kx = 0; kx < kw; ++kx) dst[ky * kw + kx] = src[ky * w + kx];
+    for (int kx = 0; kx < kw; ++kx) dst[ky * kw + kx] = src[(I)(ky * w + kx) * (I)c];
 }
 
-// dx[b][ci][y][x] = sum over (ky,kx) with 0 <= y-ky < oh, 0 <= x-kx < ow of
+// dx[(b*h + y)*w + x][ci] = sum over (ky,kx) with 0 <= y-ky < oh, 0 <= x-kx < ow of
 // dcols[patch (y-ky, x-kx)][(ci*kh + ky)*kw + kx]: a gather per input element (deterministic).
-// Thread order (b, y, x, ci) with ci fastest keeps the dcols reads of a warp contiguous-ish.
 template <typename I>
 __global__ void patches_grad_kernel(const double* __restrict__ dcols, double* __restrict__ dx, I total, int c,
                                     int h, int w, int kh, int kw, int oh, int ow) {
@@ -136,7 +138,7 @@ __global__ void patches_grad_kernel(const double* __restrict__ dcols, double* __
       acc += dcols[((b * oh + oy) * ow + ox) * K + (I)((ci * kh + ky) * kw + kx)];
     }
   }
-  dx[((b * c + ci) * h + yy) * (I)w + xx] = acc;
+  dx[i] = acc;
 }
 
 __global__ void adam_kernel(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,

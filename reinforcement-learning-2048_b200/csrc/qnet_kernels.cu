@@ -24,23 +24,25 @@
 namespace b2048 {
 namespace {
 
-constexpr int QC_THREADS = 256;           // 8 warps = 4 warp pairs
 #ifndef QC_STAGGER
 #define QC_STAGGER 20000                  // cycles; 0 disables
 #endif
 constexpr int FC1_BLK = 8;                // k-steps per register block of fc1 weights
 constexpr int IN2_STRIDE = 260;           // doubles per pooled sample row: 256 + 4 (bank spread for 64-bit loads)
 
-// shared-memory map (bytes)
-constexpr int QS_W2 = 0;                                      // [64 c1][8 n-tiles][32 lanes] doubles
-constexpr int QS_IN2 = QS_W2 + 64 * 8 * 32 * 8;               // [4 pairs][8 samples][IN2_STRIDE]
-constexpr int QS_QPART = QS_IN2 + 4 * 8 * IN2_STRIDE * 8;     // [4 pairs][8 samples][4 actions]: second warp's partial Q
-constexpr int QS_W1B = QS_QPART + 4 * 8 * 4 * 8;              // [64 c1][8]: w0 w1 w2 w3 bias - - -
-constexpr int QS_B2 = QS_W1B + 64 * 8 * 8;                    // [64]
-constexpr int QS_B3 = QS_B2 + 64 * 8;                         // [64]
-constexpr int QS_W4 = QS_B3 + 64 * 8;                         // [4][64]
-constexpr int QS_B4 = QS_W4 + 4 * 64 * 8;                     // [4]
-constexpr int QS_BYTES = QS_B4 + 4 * 8;
+// shared-memory map (bytes) for a CTA of PAIRS warp pairs (4 pairs = 256 threads, or 5 = 320 threads)
+template <int PAIRS>
+struct QS {
+  static constexpr int W2 = 0;                                   // [64 c1][8 n-tiles][32 lanes] doubles
+  static constexpr int IN2 = W2 + 64 * 8 * 32 * 8;               // [PAIRS][8 samples][IN2_STRIDE]
+  static constexpr int QPART = IN2 + PAIRS * 8 * IN2_STRIDE * 8; // [PAIRS][8 samples][4 actions]: second warp's partial Q
+  static constexpr int W1B = QPART + PAIRS * 8 * 4 * 8;          // [64 c1][8]: w0 w1 w2 w3 bias - - -
+  static constexpr int B2 = W1B + 64 * 8 * 8;                    // [64]
+  static constexpr int B3 = B2 + 64 * 8;                         // [64]
+  static constexpr int W4 = B3 + 64 * 8;                         // [4][64]
+  static constexpr int B4 = W4 + 4 * 64 * 8;                     // [4]
+  static constexpr int BYTES = B4 + 4 * 8;
+};
 
 struct QConvWeights {
   const double *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4;
@@ -73,19 +75,23 @@ __device__ __forceinline__ double cell_value(uint64_t bd, int cell, int scaling,
 // MT = conv2 row tiles per warp: 2 (4 boards per warp, 32 per CTA iteration) for long launches, 1 (2 per
 // warp, 16 per iteration; fc1 then runs on half-filled row tiles) when the launch is so short that the
 // finer granularity fills more SMs (n <= 16 * #SMs: one short round instead of one long one).
-template <int MT>
-__global__ void __launch_bounds__(QC_THREADS, 1)
+// PAIRS = warp pairs per CTA: 4, or 5 (320 threads, 200 registers each) for launches that fit one round
+// of 40-board iterations but not one of 32 (the 5 000-board batches of the update: 125 CTAs, one round).
+template <int MT, int PAIRS>
+__global__ void __launch_bounds__(64 * PAIRS, 1)
     qconv_forward_kernel(const uint64_t* __restrict__ boards, const double* __restrict__ states, int scaling,
                          const QConvWeights wts, double* __restrict__ q, int64_t n) {
   extern __shared__ __align__(16) unsigned char qsm[];
-  double* w2f = reinterpret_cast<double*>(qsm + QS_W2);
-  double* in2 = reinterpret_cast<double*>(qsm + QS_IN2);
-  double* qpart = reinterpret_cast<double*>(qsm + QS_QPART);
-  double* w1b = reinterpret_cast<double*>(qsm + QS_W1B);
-  double* b2s = reinterpret_cast<double*>(qsm + QS_B2);
-  double* b3s = reinterpret_cast<double*>(qsm + QS_B3);
-  double* w4s = reinterpret_cast<double*>(qsm + QS_W4);
-  double* b4s = reinterpret_cast<double*>(qsm + QS_B4);
+  using S = QS<PAIRS>;
+  constexpr int QC_THREADS = 64 * PAIRS;
+  double* w2f = reinterpret_cast<double*>(qsm + S::W2);
+  double* in2 = reinterpret_cast<double*>(qsm + S::IN2);
+  double* qpart = reinterpret_cast<double*>(qsm + S::QPART);
+  double* w1b = reinterpret_cast<double*>(qsm + S::W1B);
+  double* b2s = reinterpret_cast<double*>(qsm + S::B2);
+  double* b3s = reinterpret_cast<double*>(qsm + S::B3);
+  double* w4s = reinterpret_cast<double*>(qsm + S::W4);
+  double* b4s = reinterpret_cast<double*>(qsm + S::B4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, wip = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;     // fragment row (A, C) / column (B) and k index
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   }
   for (int i = tid; i < 4 * 64; i += QC_THREADS) w4s[i] = __ldg(wts.w4 + i);
   if (tid < 4) b4s[tid] = __ldg(wts.b4 + tid);
-  for (int i = tid; i < 4 * 8 * IN2_STRIDE; i += QC_THREADS) in2[i] = 0.0;   // rows a short tile never writes
+  for (int i = tid; i < PAIRS * 8 * IN2_STRIDE; i += QC_THREADS) in2[i] = 0.0;   // rows a short tile never writes
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -123,13 +129,13 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
   double* in2p = in2 + pair * 8 * IN2_STRIDE;
   double* qpartp = qpart + pair * 32;
 
-  constexpr int TILE = 16 * MT;                        // boards per CTA iteration, 2 * MT per warp
+  constexpr int TILE = 4 * MT * PAIRS;                 // boards per CTA iteration, 2 * MT per warp
   const int64_t tiles = (n + TILE - 1) / TILE;
 #if QC_STAGGER
   // Each scheduler hosts one warp of pairs 0/1 and one of pairs 2/3.  Left alone they run conv2 (DMMA
   // bound) and epilogue + fc1 (latency bound) in lockstep; starting pairs 2/3 a third of a tile later
   // lets one warp's DMMA stream cover the other's epilogue.  Only worth it for long launches.
-  if (pair >= 2 && tiles >= 8 * (int64_t)gridDim.x) {
+  if (PAIRS == 4 && pair >= 2 && tiles >= 8 * (int64_t)gridDim.x) {
     const long long t0 = clock64();
     while (clock64() - t0 < QC_STAGGER) {}
   }
@@ -275,9 +281,14 @@ __global__ void __launch_bounds__(QC_THREADS, 1)
 }  // namespace
 
 cudaError_t qnet_kernels_configure() {
-  cudaError_t e = cudaFuncSetAttribute(qconv_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(qconv_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_BYTES);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(qconv_forward_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                QS<4>::BYTES)) != cudaSuccess)
+    return e;
+  if ((e = cudaFuncSetAttribute(qconv_forward_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                QS<4>::BYTES)) != cudaSuccess)
+    return e;
+  return cudaFuncSetAttribute(qconv_forward_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS<5>::BYTES);
 }
 
 }  // namespace b2048
@@ -296,17 +307,20 @@ extern "C" int qnet_conv_forward_f64(const uint64_t* boards, const double* state
     return B2048_EINVAL;
   if (reinterpret_cast<uintptr_t>(w2) & 15u) return B2048_EINVAL;   // staged with 16-byte cp.async
   if (n == 0) return B2048_OK;
-  // rounds of CTA iterations each variant needs on this device; measured on B200 a 16-board round costs
-  // about 2/3 of a 32-board one (24 vs 36 us: half the conv2 work, the same fc1 / epilogue latency)
+  // Three variants: 16, 32 or 40 boards per CTA iteration.  Pick the one with the least estimated time =
+  // rounds of iterations on this device x measured cost of one round on B200 (24 / 36 / ~45 us: a short
+  // round still pays the full fc1 / epilogue latency, the 40-board CTA has three warps on two schedulers).
   const int64_t sms = ctx->sm_count;
-  const int64_t t32 = (n + 31) / 32, t16 = (n + 15) / 16;
-  const int64_t r32 = (t32 + sms - 1) / sms, r16 = (t16 + sms - 1) / sms;
+  const int64_t t16 = (n + 15) / 16, t32 = (n + 31) / 32, t40 = (n + 39) / 40;
+  const int64_t c16 = 24 * ((t16 + sms - 1) / sms), c32 = 36 * ((t32 + sms - 1) / sms), c40 = 45 * ((t40 + sms - 1) / sms);
   const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (67 * r16 < 100 * r32) {
-    qconv_forward_kernel<1><<<(int)(t16 < sms ? t16 : sms), QC_THREADS, QS_BYTES, st>>>(boards, states, scaling, w, q, n);
+  if (c16 < c32 && c16 <= c40) {
+    qconv_forward_kernel<1, 4><<<(int)(t16 < sms ? t16 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n);
+  } else if (c40 < c32) {
+    qconv_forward_kernel<2, 5><<<(int)(t40 < sms ? t40 : sms), 320, QS<5>::BYTES, st>>>(boards, states, scaling, w, q, n);
   } else {
-    qconv_forward_kernel<2><<<(int)(t32 < sms ? t32 : sms), QC_THREADS, QS_BYTES, st>>>(boards, states, scaling, w, q, n);
+    qconv_forward_kernel<2, 4><<<(int)(t32 < sms ? t32 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n);
   }
   return (int)cudaGetLastError();
 }

@@ -201,7 +201,7 @@ def test_fused_conv_forward_matches_reference_q_values(cuda, golden_dir):
                                atol=1e-9 * np.abs(d["q_next_online"]).max())
 
 
-@pytest.mark.parametrize("n", [1, 3, 31, 32, 33, 257, 4736, 70001])
+@pytest.mark.parametrize("n", [1, 3, 31, 32, 33, 257, 2368, 4736, 5000, 5919, 70001])
 def test_fused_conv_forward_sizes_and_scalings(cuda, n):
     """Ragged sizes (partial tiles, partial warp pairs, more tiles than SMs) and both input scalings
     against the torch float64 module on the same inputs."""
