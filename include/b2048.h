@@ -214,11 +214,13 @@ int ddqn_target_loss(const double* q_next_online, const double* q_next_target, c
  * consecutive convolutions need no layout round trip.
  *   conv_patches_f64:      x [n*h*w, c] -> cols [n*oh*ow, c*kh*kw], (c,kh,kw) order like conv.weight
  *   conv_patches_grad_f64: d cols -> d x [n*h*w, c] (each input element sums the <= kh*kw patches
- *                          that read it: a gather, deterministic, no atomics) */
+ *                          that read it: a gather, deterministic, no atomics).  act_cols (nullable):
+ *                          the forward patch matrix of a post-ReLU activation; d x is then also
+ *                          masked with (activation > 0), i.e. the gradient of "ReLU, then im2col". */
 int conv_patches_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
                      void* stream);
-int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
-                          int kw, void* stream);
+int conv_patches_grad_f64(const double* dcols, const double* act_cols, double* dx, int64_t n, int c, int h,
+                          int w, int kh, int kw, void* stream);
 
 /* Fused Adam step on one flat float64 parameter buffer (= optimizer.step() of torch.optim.Adam
  * without weight decay / amsgrad, configs/double_dqn_*.py: Adam(lr=1e-2); src/dqn_lib.py:163).
@@ -282,6 +284,17 @@ int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scal
                           const double* b1, const double* w2, const double* b2, const double* w3,
                           const double* b3, const double* w4, const double* b4, double* q, int64_t n,
                           void* stream);
+
+/* The same forward for Q(s) of train_step (src/dqn_lib.py:146-150), where a backward pass follows: it
+ * also writes what that pass needs — patches2 [4n,256] = the second convolution's input in im2col form
+ * (row = board*4 + output position, column = channel*4 + tap; post-ReLU, exactly the operand the kernel
+ * builds on the fly), act2 [n,256] = relu(conv2) in nn.Flatten order, act3 [n,64] = relu(fc1).
+ * states: float64 [n,16].  The backward is layer_wgrad_small_f64 / layer_wgrad64_f64 on these plus
+ * cuBLAS DGEMMs for the input gradients (b2048/qfused.py). */
+int qnet_conv_forward_train_f64(const double* states, const double* w1, const double* b1, const double* w2,
+                                const double* b2, const double* w3, const double* b3, const double* w4,
+                                const double* b4, double* q, double* patches2, double* act2, double* act3,
+                                int64_t n, void* stream);
 
 /* ---- weight + bias gradient of a layer with a tiny weight matrix ----------------------------------- */
 

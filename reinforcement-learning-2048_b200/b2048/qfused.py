@@ -79,6 +79,92 @@ class FusedConvQ:
         return self._run(None, x, "log2", n, out)
 
 
+class _ConvQTrain(torch.autograd.Function):
+    """Q(s) of the conv Q-network with a hand-built backward (train_step, src/dqn_lib.py:146-161).
+
+    forward: one K6 launch that also stores the three activations the backward needs (the second
+    convolution's im2col input, relu(conv2), relu(fc1)).  backward: per layer the weight / bias gradient
+    kernels of csrc/wgrad_kernels.cu (K7) on those stored matrices, cuBLAS DGEMMs for the input gradients,
+    ATen's threshold_backward for the ReLU masks and one masked col2im.  Same arithmetic as autograd on
+    the nn.Sequential, different summation order (1e-10 relative on the gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4):
+        n = x.shape[0]
+        dev = _dev(x)
+        _lib.init(dev)
+        kw = dict(dtype=torch.float64, device=x.device)
+        q, p2 = torch.empty((n, 4), **kw), torch.empty((4 * n, 256), **kw)
+        a2, a3 = torch.empty((n, 256), **kw), torch.empty((n, 64), **kw)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().qnet_conv_forward_train_f64(
+                _ptr(x), *[_ptr(p) for p in (w1, b1, w2, b2, w3, b3, w4, b4)], _ptr(q), _ptr(p2), _ptr(a2), _ptr(a3), n,
+                _stream(x)), "qnet_conv_forward_train_f64")
+        ctx.save_for_backward(x, w2, w3, w4, p2, a2, a3)
+        return q
+
+    @staticmethod
+    def backward(ctx, gq):
+        x, w2, w3, w4, p2, a2, a3 = ctx.saved_tensors
+        n = x.shape[0]
+        dev = _dev(x)
+        L = _lib.lib()
+        kw = dict(dtype=torch.float64, device=x.device)
+        st = _stream(x)
+
+        def wgrad(g, xin, c, k):
+            gw, gb = torch.empty((c, k), **kw), torch.empty(c, **kw)
+            if c * k <= 1024:
+                scratch = torch.empty(L.layer_wgrad_small_scratch_elems(g.shape[0], c, k), **kw)
+                _lib.check(L.layer_wgrad_small_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], c, k,
+                                                   st), "layer_wgrad_small_f64")
+            else:
+                scratch = torch.empty(L.layer_wgrad64_scratch_elems(g.shape[0], k), **kw)
+                _lib.check(L.layer_wgrad64_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], k, st),
+                           "layer_wgrad64_f64")
+            return gw, gb
+
+        relu_grad = torch.ops.aten.threshold_backward
+        with torch.cuda.device(dev):
+            g4 = gq.contiguous()                                              # [n, 4]
+            gw4, gb4 = wgrad(g4, a3, 4, 64)
+            g3 = relu_grad(torch.mm(g4, w4), a3, 0.0)                         # [n, 64]
+            gw3, gb3 = wgrad(g3, a2, 64, 256)
+            g2f = relu_grad(torch.mm(g3, w3), a2, 0.0)                        # [n, 256], feature = channel*4 + position
+            g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
+            gw2, gb2 = wgrad(g2, p2, 64, 256)
+            gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
+            g1 = torch.empty((9 * n, 64), **kw)                               # relu'(conv1) * col2im, one kernel
+            _lib.check(L.conv_patches_grad_f64(_ptr(gp2), _ptr(p2), _ptr(g1), n, 64, 3, 3, 2, 2, st), "conv_patches_grad_f64")
+            p1 = torch.empty((9 * n, 4), **kw)                                # conv1's patches of the input boards
+            _lib.check(L.conv_patches_f64(_ptr(x), _ptr(p1), n, 1, 4, 4, 2, 2, st), "conv_patches_f64")
+            gw1, gb1 = wgrad(g1, p1, 64, 4)
+        return None, gw1.view(64, 1, 2, 2), gb1, gw2.view(64, 64, 2, 2), gb2, gw3, gb3, gw4, gb4
+
+
+class TrainableConvQ(nn.Module):
+    """The reference's conv Q-network as a module whose forward is K6 and whose backward is K7 + cuBLAS
+    (`_ConvQTrain`); without gradients it is the plain fused forward.  Wraps the caller's nn.Sequential:
+    the parameters are its own tensors."""
+
+    def __init__(self, net: nn.Sequential):
+        super().__init__()
+        if not matches(net):
+            raise ValueError("TrainableConvQ needs the float64 conv Q-network of configs/double_dqn_conv.py on a CUDA device")
+        self.net = net
+        self._fused = FusedConvQ(net)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n = x.shape[0]
+        x2 = x.reshape(n, 16)
+        if not (x2.is_cuda and x2.dtype == torch.float64 and x2.is_contiguous()) or x.requires_grad:
+            return self.net(x)                       # e.g. a gradient w.r.t. the input is asked for: plain autograd
+        if n == 0 or not (torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters())):
+            return self._fused(x2)
+        c1, _, c2, _, _, l1, _, l2 = self.net
+        return _ConvQTrain.apply(x2, c1.weight, c1.bias, c2.weight, c2.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+
+
 def accelerate_inference(net: nn.Module):
     """The fastest no-gradient evaluator for `net`: the fused kernel for the reference's conv
     Q-network, otherwise `qnet.accelerate(net)` (float64 GEMM path)."""

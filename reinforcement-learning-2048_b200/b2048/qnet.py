@@ -41,7 +41,7 @@ class _Patches(torch.autograd.Function):
         dcols = dcols.contiguous()
         dx = torch.empty((n * h * w, c), dtype=dcols.dtype, device=dcols.device)
         with torch.cuda.device(dcols.device):
-            _lib.check(_lib.lib().conv_patches_grad_f64(_ptr(dcols), _ptr(dx), n, c, h, w, kh, kw, _stream(dcols)),
+            _lib.check(_lib.lib().conv_patches_grad_f64(_ptr(dcols), None, _ptr(dx), n, c, h, w, kh, kw, _stream(dcols)),
                        "conv_patches_grad_f64")
         return dx, None, None, None, None, None, None
 
@@ -152,6 +152,10 @@ class FastQNet(nn.Module):
 
 
 def accelerate(net: nn.Module) -> nn.Module:
-    """FastQNet for float64 CUDA Sequentials of plain small convolutions + ReLU / Flatten / Linear (the
-    reference's conv config), otherwise the module itself."""
+    """The fastest evaluator with gradients for `net`: `qfused.TrainableConvQ` (K6 forward, K7 backward)
+    for the reference's conv Q-network, FastQNet for other float64 CUDA Sequentials of plain small
+    convolutions + ReLU / Flatten / Linear, otherwise the module itself."""
+    from . import qfused
+    if qfused.matches(net):
+        return qfused.TrainableConvQ(net)
     return FastQNet(net) if FastQNet.supports(net) else net

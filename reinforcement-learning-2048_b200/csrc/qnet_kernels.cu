@@ -77,10 +77,18 @@ __device__ __forceinline__ double cell_value(uint64_t bd, int cell, int scaling,
 // finer granularity fills more SMs (n <= 16 * #SMs: one short round instead of one long one).
 // PAIRS = warp pairs per CTA: 4, or 5 (320 threads, 200 registers each) for launches that fit one round
 // of 40-board iterations but not one of 32 (the 5 000-board batches of the update: 125 CTAs, one round).
-template <int MT, int PAIRS>
+// SAVE = also write what the backward pass needs (train_step, src/dqn_lib.py:146-161): the conv2 input in
+// im2col form (exactly the A operand this kernel builds on the fly), and the post-ReLU outputs of conv2
+// (nn.Flatten order) and fc1.
+struct QConvSaved {
+  double* patches2;   // [4n, 256]: row (board, conv2 position), column c1*4 + tap = relu(conv1) at that tap
+  double* act2;       // [n, 256]:  relu(conv2) in nn.Flatten order (channel*4 + position)
+  double* act3;       // [n, 64]:   relu(fc1)
+};
+template <int MT, int PAIRS, bool SAVE>
 __global__ void __launch_bounds__(64 * PAIRS, 1)
     qconv_forward_kernel(const uint64_t* __restrict__ boards, const double* __restrict__ states, int scaling,
-                         const QConvWeights wts, double* __restrict__ q, int64_t n) {
+                         const QConvWeights wts, double* __restrict__ q, int64_t n, const QConvSaved sv) {
   extern __shared__ __align__(16) unsigned char qsm[];
   using S = QS<PAIRS>;
   constexpr int QC_THREADS = 64 * PAIRS;
@@ -184,8 +192,11 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
       const double bias = w1b[c1 * 8 + 4];
       double a[MT];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+      for (int mt = 0; mt < MT; ++mt) {
         a[mt] = relu(fma(x[mt][3], w.w, fma(x[mt][2], w.z, fma(x[mt][1], w.y, fma(x[mt][0], w.x, bias)))));
+        if (SAVE && s_warp + mt * 2 + (fr >> 2) < n)       // patch row 4*board + position = 4*s_warp + 8*mt + fr
+          sv.patches2[(4 * s_warp + 8 * mt + fr) * 256 + c1 * 4 + fk] = a[mt];
+      }
       const double* bf = w2f + c1 * 256 + lane;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -213,6 +224,14 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
       }
     }
     pair_barrier(pair);
+    if (SAVE) {   // the pair's pooled rows are contiguous boards: 64 threads copy them out, coalesced
+      const int64_t s_pair = tile * TILE + pair * (4 * MT);
+      const int t64 = wip * 32 + lane;
+      for (int i = t64; i < 4 * MT * 256; i += 64) {
+        const int r = i >> 8, c = i & 255;
+        if (s_pair + r < n) sv.act2[(s_pair + r) * 256 + c] = in2p[r * IN2_STRIDE + c];
+      }
+    }
 
     // ---- fc1: the pair's pooled boards (8 row slots) x 32 of the 64 hidden units per warp, K = 256; the weights stream from
     // L2 through two register blocks of FC1_BLK k-steps (load block j+1 while block j multiplies) ------
@@ -257,6 +276,8 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
     for (int nt = 0; nt < 4; ++nt) {
       const int hh = wip * 32 + nt * 8 + 2 * fk;
       const double v0 = relu(h[nt][0]), v1 = relu(h[nt][1]);
+      if (SAVE && fr < 4 * MT && tile * TILE + pair * (4 * MT) + fr < n)
+        *reinterpret_cast<double2*>(sv.act3 + (tile * TILE + pair * (4 * MT) + fr) * 64 + hh) = make_double2(v0, v1);
 #pragma unroll
       for (int a = 0; a < 4; ++a) part[a] = fma(v1, w4s[a * 64 + hh + 1], fma(v0, w4s[a * 64 + hh], part[a]));
     }
@@ -280,15 +301,19 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
 
 }  // namespace
 
+template <int MT, int PAIRS, bool SAVE>
+cudaError_t configure_one() {
+  return cudaFuncSetAttribute(qconv_forward_kernel<MT, PAIRS, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              QS<PAIRS>::BYTES);
+}
+
 cudaError_t qnet_kernels_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(qconv_forward_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                QS<4>::BYTES)) != cudaSuccess)
-    return e;
-  if ((e = cudaFuncSetAttribute(qconv_forward_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                QS<4>::BYTES)) != cudaSuccess)
-    return e;
-  return cudaFuncSetAttribute(qconv_forward_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, QS<5>::BYTES);
+  if ((e = configure_one<1, 4, false>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 4, false>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 5, false>()) != cudaSuccess) return e;
+  if ((e = configure_one<2, 4, true>()) != cudaSuccess) return e;
+  return configure_one<2, 5, true>();
 }
 
 }  // namespace b2048
@@ -316,11 +341,35 @@ extern "C" int qnet_conv_forward_f64(const uint64_t* boards, const double* state
   const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c16 < c32 && c16 <= c40) {
-    qconv_forward_kernel<1, 4><<<(int)(t16 < sms ? t16 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n);
+    qconv_forward_kernel<1, 4, false><<<(int)(t16 < sms ? t16 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n, QConvSaved{});
   } else if (c40 < c32) {
-    qconv_forward_kernel<2, 5><<<(int)(t40 < sms ? t40 : sms), 320, QS<5>::BYTES, st>>>(boards, states, scaling, w, q, n);
+    qconv_forward_kernel<2, 5, false><<<(int)(t40 < sms ? t40 : sms), 320, QS<5>::BYTES, st>>>(boards, states, scaling, w, q, n, QConvSaved{});
   } else {
-    qconv_forward_kernel<2, 4><<<(int)(t32 < sms ? t32 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n);
+    qconv_forward_kernel<2, 4, false><<<(int)(t32 < sms ? t32 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n, QConvSaved{});
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int qnet_conv_forward_train_f64(const double* states, const double* w1, const double* b1, const double* w2,
+                                           const double* b2, const double* w3, const double* b3, const double* w4,
+                                           const double* b4, double* q, double* patches2, double* act2, double* act3,
+                                           int64_t n, void* stream) {
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  if (n <= 0 || !states || !q || !patches2 || !act2 || !act3 || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4 ||
+      ((reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(act3)) & 15u))
+    return B2048_EINVAL;
+  const int64_t sms = ctx->sm_count;
+  const int64_t t32 = (n + 31) / 32, t40 = (n + 39) / 40;
+  const int64_t c32 = 36 * ((t32 + sms - 1) / sms), c40 = 45 * ((t40 + sms - 1) / sms);
+  const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
+  const QConvSaved sv{patches2, act2, act3};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c40 < c32) {
+    qconv_forward_kernel<2, 5, true><<<(int)(t40 < sms ? t40 : sms), 320, QS<5>::BYTES, st>>>(nullptr, states, 0, w, q, n, sv);
+  } else {
+    qconv_forward_kernel<2, 4, true><<<(int)(t32 < sms ? t32 : sms), 256, QS<4>::BYTES, st>>>(nullptr, states, 0, w, q, n, sv);
   }
   return (int)cudaGetLastError();
 }

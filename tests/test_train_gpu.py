@@ -134,14 +134,26 @@ def test_updater_graph_equals_eager_and_learns(cuda):
     assert all(torch.equal(p, q) for p, q in zip(c.model.parameters(), c.target.parameters()))
 
 
-def test_fast_conv_forward_equals_cudnn_path(cuda):
-    """Conv2d layers evaluated as float64 GEMMs: same outputs and gradients as nn.Conv2d (1e-12)."""
-    from b2048.qnet import accelerate
+def _other_conv_model():
+    from torch import nn   # not the reference's widths: exercises the generic FastQNet path
+    return nn.Sequential(nn.Conv2d(1, 32, kernel_size=2), nn.ReLU(), nn.Conv2d(32, 64, kernel_size=2), nn.ReLU(),
+                         nn.Flatten(), nn.Linear(2 * 2 * 64, 48), nn.ReLU(), nn.Linear(48, 4)).double()
+
+
+@pytest.mark.parametrize("which,n", [("reference", 5000), ("reference", 33), ("reference", 6000), ("other", 5000), ("other", 7)])
+def test_fast_conv_forward_equals_cudnn_path(cuda, which, n):
+    """The conv Q-network with gradients — reference architecture: K6 forward with saved activations +
+    hand-built backward (K7, masked col2im, cuBLAS); any other small conv net: FastQNet (patch gathers +
+    DGEMMs + K7) — gives the same outputs and parameter gradients as the plain torch float64 module
+    (1e-12 / 1e-10 relative), bit-identically from run to run."""
+    from b2048.qfused import TrainableConvQ
+    from b2048.qnet import FastQNet, accelerate
     torch.manual_seed(3)
-    net = conv_model().to(cuda)
+    net = (conv_model() if which == "reference" else _other_conv_model()).to(cuda)
     fast = accelerate(net)
-    assert fast is not net and accelerate(dense_model()) .__class__.__name__ == "Sequential"
-    x = torch.randint(0, 12, (5000, 1, 4, 4), device=cuda).double()
+    assert isinstance(fast, TrainableConvQ if which == "reference" else FastQNet)
+    assert accelerate(dense_model()).__class__.__name__ == "Sequential"
+    x = torch.randint(0, 12, (n, 1, 4, 4), device=cuda).double()
     a, b = net(x), fast(x)
     np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().cpu().numpy(), rtol=1e-12, atol=1e-13)
     a.square().sum().backward()
@@ -149,8 +161,15 @@ def test_fast_conv_forward_equals_cudnn_path(cuda):
     for p in net.parameters():
         p.grad = None
     fast(x).square().sum().backward()
-    for u, p in zip(g1, net.parameters()):
-        np.testing.assert_allclose(p.grad.cpu().numpy(), u.cpu().numpy(), rtol=1e-10, atol=1e-10 * float(u.abs().max()))
+    g2 = [p.grad.clone() for p in net.parameters()]
+    for u, v in zip(g1, g2):
+        np.testing.assert_allclose(v.cpu().numpy(), u.cpu().numpy(), rtol=1e-10, atol=1e-10 * float(u.abs().max()))
+    for p in net.parameters():
+        p.grad = None
+    fast(x).square().sum().backward()
+    assert all(torch.equal(p.grad, v) for p, v in zip(net.parameters(), g2))       # fixed summation order
+    with torch.no_grad():
+        np.testing.assert_allclose(fast(x).cpu().numpy(), a.detach().cpu().numpy(), rtol=1e-12, atol=1e-13)
 
 
 @pytest.mark.parametrize("rows,c,k", [(45000, 64, 4), (5000, 4, 64), (1, 2, 3), (127, 16, 64), (128, 64, 16), (40001, 1, 1)])
