@@ -133,7 +133,7 @@ __global__ void patches_grad_kernel(const double* __restrict__ dcols, const doub
   const I b = t / (I)h;
   const I K = (I)c * kh * kw;
   double acc = 0.0;
-  bool alive = act_cols == nullptr;
+  bool alive = true, checked = act_cols == nullptr;
   for (int ky = 0; ky < kh; ++ky) {
     const int oy = yy - ky;
     if (oy < 0 || oy >= oh) continue;
@@ -142,7 +142,10 @@ __global__ void patches_grad_kernel(const double* __restrict__ dcols, const doub
       if (ox < 0 || ox >= ow) continue;
       const I at = ((b * oh + oy) * ow + ox) * K + (I)((ci * kh + ky) * kw + kx);
       acc += dcols[at];
-      if (!alive && act_cols[at] > 0.0) alive = true;
+      if (!checked) {          // every contributing entry holds the same activation: look at the first only
+        checked = true;
+        alive = act_cols[at] > 0.0;
+      }
     }
   }
   dx[i] = alive ? acc : 0.0;

@@ -129,12 +129,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 
 __global__ void __launch_bounds__(256, 1)
     wgrad_dmma_kernel(const double* __restrict__ g, const double* __restrict__ x, double* __restrict__ partials,
-                      int64_t rows, int K, int64_t rows_per_block) {
+                      int64_t rows, int K) {
   extern __shared__ __align__(16) double wsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
   const int O = 64 * K;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  // CTA b takes row tiles b, b + grid, b + 2*grid, ...: a fixed assignment (the partial sums do not depend
+  // on scheduling) without a ragged tail per CTA
+  const int64_t r1 = rows, ntiles = (rows + WT_ROWS - 1) / WT_ROWS;
   const bool active = warp * 32 < K;
 
   auto stage = [&](int buf, int64_t t0) {     // rows [t0, t0+32) -> buffer `buf`; rows past r1 become zeros
@@ -162,10 +163,10 @@ __global__ void __launch_bounds__(256, 1)
   double accb = 0.0;
 
   int buf = 0;
-  if (r0 < r1) stage(0, r0);
-  for (int64_t t0 = r0; t0 < r1; t0 += WT_ROWS) {
-    if (t0 + WT_ROWS < r1) {
-      stage(buf ^ 1, t0 + WT_ROWS);
+  if (blockIdx.x < ntiles) stage(0, (int64_t)blockIdx.x * WT_ROWS);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile + gridDim.x < ntiles) {
+      stage(buf ^ 1, (tile + gridDim.x) * WT_ROWS);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -265,9 +266,8 @@ extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, d
   if (!ctx) return err;
   if (ctx->sm_count > 160) return B2048_EINVAL;
   const int64_t blocks = wt_blocks(rows, ctx->sm_count);
-  int64_t rpb = (rows + blocks - 1) / blocks;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K, rpb);
+  wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int O = 64 * K;
