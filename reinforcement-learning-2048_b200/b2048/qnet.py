@@ -1,17 +1,19 @@
-"""Float64 Q-network forward for tiny boards.
+"""Float64 Q-networks with gradients for tiny boards (the autograd path of train_step,
+src/dqn_lib.py:146-161).
 
-The reference's conv net (configs/double_dqn_conv.py:19-28) is two 2x2 convolutions on a 4x4 board.
-cuDNN has no fast float64 path for it (12.9 ms per update at batch 5000 on B200, 0.3 TFLOP/s);
-written as patch-gather + one float64 GEMM per layer (cuBLAS DGEMM) the same arithmetic runs an
-order of magnitude faster.  The weights stay in the caller's nn.Sequential — the same parameter
-tensors are used, so training the wrapper trains the original module (checkpoints, target sync and
-`Experiment.save` keep working) — and only the summation order inside a convolution changes
-(differences ~1e-15 relative, inside the 1e-9 parity gate).
+`accelerate(net)` picks the evaluator: the reference's conv Q-network (configs/double_dqn_conv.py:19-28)
+gets `qfused.TrainableConvQ` (K6 forward with saved activations, hand-built backward); any other small
+conv net gets `FastQNet` below.  cuDNN has no fast float64 path for 2x2 convolutions on a 4x4 board
+(12.9 ms per update at batch 5000 on B200, 0.3 TFLOP/s); written as patch gather + one float64 GEMM per
+layer (cuBLAS DGEMM) on row-matrix activations, with the weight / bias gradients from the K7 kernels,
+the same arithmetic runs an order of magnitude faster.  The weights stay in the caller's nn.Sequential
+— the same parameter tensors are used, so training the wrapper trains the original module (checkpoints,
+target sync and `Experiment.save` keep working) — and only the summation order changes (differences
+~1e-15 relative, inside the 1e-9 parity gate).
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 

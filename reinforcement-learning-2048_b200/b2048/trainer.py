@@ -1,5 +1,7 @@
-"""Double-DQN updates at scale: GPU replay sampling (K2) + float64 Q-network forwards (torch) +
-fused target/loss (K3) + backward + gradient allreduce (NCCL) + Adam, captured in one CUDA graph.
+"""Double-DQN updates at scale, captured in one CUDA graph: GPU replay sampling (K2), the float64
+Q-network forwards (conv config: the fused kernel K6, with saved activations for Q(s); otherwise torch),
+fused target / loss (K3), backward (conv config: K7 weight gradients + cuBLAS), gradient exchange + Adam
+(one GPU: fused Adam kernel; several: the NVLink peer-memory kernel K5, or NCCL).
 
 `DDQNUpdater.update()` is the "real" update (zero_grad -> backward -> allreduce -> step); the
 reference's train_step order, which never changes the weights, is what the drop-in
