@@ -264,6 +264,26 @@ def secondary_metrics(args, dev, rank, world, barrier):
             "workload": f"{name} Q-net float64, batch 5000/GPU, replay 15000, gamma 0.8 (f32), Double DQN, Adam; "
                         "sample+3 fwd+fused loss+bwd+allreduce+Adam in one CUDA graph",
             "updates_per_sec": 1e3 / ms, "ms_per_update": ms, "global_batch": 5000 * world}
+    # the whole loop: batched Double-DQN training with the reference's conv config and schedule
+    # (train_batched: epsilon-greedy rollouts on K6 -> replay ring -> one update per finished episode)
+    import time
+    from b2048.train import TrainConfig, train_batched
+    torch.manual_seed(0)
+    cfg = TrainConfig(n_envs=4096, no_episodes=8000, no_episodes_before_training=700, no_episodes_to_reach_epsilon=1000,
+                      batch_size=5000, learning_rate=1e-4, max_updates_per_step=8, seed=11)
+    barrier()
+    t0 = time.perf_counter()
+    st = train_batched(conv_qnet().to(dev), cfg, device=dev)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    out["train_batched_conv"] = {
+        "workload": "reference conv config end to end: 4096 concurrent games per GPU, 8000 episodes per GPU, one update "
+                    "(batch 5000/GPU) per finished episode after 700, target sync every 100; wall clock incl. graph capture",
+        "episodes_per_sec": world * st["games"] / dt, "updates_per_sec": st["updates"] / dt,
+        "env_steps_per_sec": world * st["steps"] * cfg.n_envs / dt, "seconds": dt}
     return out
 
 

@@ -57,8 +57,8 @@ def epsilon_for(ep: int, cfg: TrainConfig) -> float:
 
 
 def train_batched(model: torch.nn.Module, cfg: TrainConfig, device="cuda", log_every: int = 0, on_log=None) -> dict:
-    """Runs until `cfg.no_episodes` games have finished on this rank.  Returns the rollout
-    statistics plus the update / target-sync counts."""
+    """Runs until `cfg.no_episodes` games have finished on this rank (with several ranks: on every
+    rank).  Returns the rollout statistics plus the update / target-sync counts."""
     rank, world = bdist.world()
     dev = torch.device(device)
     base, _ = bdist.shard(cfg.n_envs * world, rank, world)
@@ -68,7 +68,8 @@ def train_batched(model: torch.nn.Module, cfg: TrainConfig, device="cuda", log_e
                           use_double=cfg.use_double_dqn, conv=cfg.conv, use_graph=cfg.use_graph, seed=cfg.seed + 1)
     episodes = updates = syncs = owed = steps = 0
     last_loss = None
-    while episodes < cfg.no_episodes:
+    running = True
+    while running:
         venv.step(model=updater.i_model, epsilon=epsilon_for(episodes, cfg), replay=ring)
         steps += 1
         finished = int(venv.totals[0].item())            # one scalar read-back per step
@@ -79,10 +80,11 @@ def train_batched(model: torch.nn.Module, cfg: TrainConfig, device="cuda", log_e
         crossings = (finished - 1) // k - (episodes - 1) // k          # episode indices in [episodes, finished) divisible by K
         episodes = finished
         n_upd = min(owed, cfg.max_updates_per_step)
-        if world > 1:                                    # same number of collective launches on every rank
-            t = torch.tensor([n_upd], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            n_upd = int(t.item())
+        running = episodes < cfg.no_episodes
+        if world > 1:        # same number of collective launches on every rank, and a collective stop:
+            t = torch.tensor([n_upd, -int(running)], device=dev)     # ranks that are through keep playing
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)                 # until the slowest one is (MIN of -running)
+            n_upd, running = int(t[0].item()), bool(-int(t[1].item()))
         for _ in range(n_upd):
             last_loss = updater.update()
         owed -= n_upd
