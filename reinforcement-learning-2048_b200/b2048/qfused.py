@@ -158,7 +158,8 @@ class TrainableConvQ(nn.Module):
         n = x.shape[0]
         x2 = x.reshape(n, 16)
         if not (x2.is_cuda and x2.dtype == torch.float64 and x2.is_contiguous()) or x.requires_grad:
-            return self.net(x)                       # e.g. a gradient w.r.t. the input is asked for: plain autograd
+            from .qnet import FastQNet               # e.g. a gradient w.r.t. the input is asked for: GEMM path
+            return FastQNet(self.net)(x.reshape(n, 1, 4, 4)) if FastQNet.supports(self.net) else self.net(x)
         if n == 0 or not (torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters())):
             return self._fused(x2)
         c1, _, c2, _, _, l1, _, l2 = self.net

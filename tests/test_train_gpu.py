@@ -170,6 +170,11 @@ def test_fast_conv_forward_equals_cudnn_path(cuda, which, n):
     assert all(torch.equal(p.grad, v) for p, v in zip(net.parameters(), g2))       # fixed summation order
     with torch.no_grad():
         np.testing.assert_allclose(fast(x).cpu().numpy(), a.detach().cpu().numpy(), rtol=1e-12, atol=1e-13)
+    xg = x.clone().requires_grad_(True)                   # input gradient requested: generic autograd path
+    fast(xg).square().sum().backward()
+    xr = x.clone().requires_grad_(True)
+    net(xr).square().sum().backward()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-10, atol=1e-10 * float(xr.grad.abs().max()))
 
 
 @pytest.mark.parametrize("rows,c,k", [(45000, 64, 4), (5000, 4, 64), (1, 2, 3), (127, 16, 64), (128, 64, 16), (40001, 1, 1)])
