@@ -303,7 +303,8 @@ int qnet_conv_forward_train_f64(const double* states, const double* w1, const do
  * output layer (Linear(64,4)) of src/configs/double_dqn_conv.py:19-28 — a tall-skinny reduction over
  * 45 000 / 5 000 rows that cuBLAS + ATen run on one or two CTAs.  g [rows,C], x [rows,K] row-major
  * float64, C, K <= 64, C*K <= 1024; dw [C,K], db [C]; fixed summation order (bit-reproducible).
- * scratch: layer_wgrad_small_scratch_elems(rows, C, K) doubles. */
+ * scratch: layer_wgrad_small_scratch_elems(rows, C, K) doubles (for the current, initialised device; 0 on
+ * bad arguments). */
 int64_t layer_wgrad_small_scratch_elems(int64_t rows, int C, int K);
 int layer_wgrad_small_f64(const double* g, const double* x, double* dw, double* db, double* scratch,
                           int64_t rows, int C, int K, void* stream);

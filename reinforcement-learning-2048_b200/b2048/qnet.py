@@ -26,8 +26,9 @@ class _Patches(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n, c, h, w, kh, kw):
         from . import _lib
-        from .env import _ptr, _stream
+        from .env import _dev, _ptr, _stream
         x = x.contiguous()
+        _lib.init(_dev(x))
         ctx.geom = (n, c, h, w, kh, kw)
         cols = torch.empty((n * (h - kh + 1) * (w - kw + 1), c * kh * kw), dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
@@ -73,11 +74,12 @@ class _AddmmOwnWgrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         from . import _lib
-        from .env import _ptr, _stream
+        from .env import _dev, _ptr, _stream
         x, weight = ctx.saved_tensors
         gy = gy.contiguous()
         rows, c = gy.shape
         k = x.shape[1]
+        _lib.init(_dev(gy))
         L = _lib.lib()
         gw = torch.empty((c, k), dtype=gy.dtype, device=gy.device)
         gb = torch.empty(c, dtype=gy.dtype, device=gy.device)

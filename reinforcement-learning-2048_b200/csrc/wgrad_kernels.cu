@@ -225,8 +225,10 @@ int64_t wt_blocks(int64_t rows, int sms) {
 using namespace b2048;
 
 extern "C" int64_t layer_wgrad_small_scratch_elems(int64_t rows, int C, int K) {
-  (void)rows;
-  return 160 * ((int64_t)C * K + C);   // upper bound of wg_blocks() on any supported device (<= 160 SMs)
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);          // one partial result per block of the current device's launch
+  if (!ctx || rows <= 0 || C <= 0 || K <= 0) return 0;
+  return wg_blocks(rows, ctx->sm_count) * ((int64_t)C * K + C);
 }
 
 extern "C" int layer_wgrad_small_f64(const double* g, const double* x, double* dw, double* db, double* scratch,
@@ -237,7 +239,6 @@ extern "C" int layer_wgrad_small_f64(const double* g, const double* x, double* d
   int err = 0;
   DeviceCtx* ctx = current_ctx(&err);
   if (!ctx) return err;
-  if (ctx->sm_count > 160) return B2048_EINVAL;
   const int64_t blocks = wg_blocks(rows, ctx->sm_count);
   const int64_t rpb = (rows + blocks - 1) / blocks;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -252,8 +253,10 @@ extern "C" int layer_wgrad_small_f64(const double* g, const double* x, double* d
 }
 
 extern "C" int64_t layer_wgrad64_scratch_elems(int64_t rows, int K) {
-  (void)rows;
-  return 160 * (64 * (int64_t)K + 64);
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx || rows <= 0 || K <= 0) return 0;
+  return wt_blocks(rows, ctx->sm_count) * (64 * (int64_t)K + 64);
 }
 
 extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, double* db, double* scratch,
@@ -264,7 +267,6 @@ extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, d
   int err = 0;
   DeviceCtx* ctx = current_ctx(&err);
   if (!ctx) return err;
-  if (ctx->sm_count > 160) return B2048_EINVAL;
   const int64_t blocks = wt_blocks(rows, ctx->sm_count);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K);
