@@ -79,6 +79,16 @@ class FusedConvQ:
         return self._run(None, x, "log2", n, out)
 
 
+_SIDE = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class _ConvQTrain(torch.autograd.Function):
     """Q(s) of the conv Q-network with a hand-built backward (train_step, src/dqn_lib.py:146-161).
 
@@ -110,35 +120,45 @@ class _ConvQTrain(torch.autograd.Function):
         dev = _dev(x)
         L = _lib.lib()
         kw = dict(dtype=torch.float64, device=x.device)
-        st = _stream(x)
+        main = torch.cuda.current_stream(x.device)
+        side = _side_stream(x.device)
+        st = main.cuda_stream
 
-        def wgrad(g, xin, c, k):
+        def wgrad(g, xin, c, k, stream):
             gw, gb = torch.empty((c, k), **kw), torch.empty(c, **kw)
             if c * k <= 1024:
                 scratch = torch.empty(L.layer_wgrad_small_scratch_elems(g.shape[0], c, k), **kw)
                 _lib.check(L.layer_wgrad_small_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], c, k,
-                                                   st), "layer_wgrad_small_f64")
+                                                   stream), "layer_wgrad_small_f64")
             else:
                 scratch = torch.empty(L.layer_wgrad64_scratch_elems(g.shape[0], k), **kw)
-                _lib.check(L.layer_wgrad64_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], k, st),
+                _lib.check(L.layer_wgrad64_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], k, stream),
                            "layer_wgrad64_f64")
             return gw, gb
+
+        def wgrad_aside(g, xin, c, k):
+            """The weight gradients are leaves of the dependency chain g4 -> g3 -> g2 -> g1: they run on a
+            side stream next to the input-gradient GEMMs (fork here, join at the end; capturable)."""
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                return wgrad(g, xin, c, k, side.cuda_stream)
 
         relu_grad = torch.ops.aten.threshold_backward
         with torch.cuda.device(dev):
             g4 = gq.contiguous()                                              # [n, 4]
-            gw4, gb4 = wgrad(g4, a3, 4, 64)
+            gw4, gb4 = wgrad_aside(g4, a3, 4, 64)
             g3 = relu_grad(torch.mm(g4, w4), a3, 0.0)                         # [n, 64]
-            gw3, gb3 = wgrad(g3, a2, 64, 256)
+            gw3, gb3 = wgrad_aside(g3, a2, 64, 256)
             g2f = relu_grad(torch.mm(g3, w3), a2, 0.0)                        # [n, 256], feature = channel*4 + position
             g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
-            gw2, gb2 = wgrad(g2, p2, 64, 256)
+            gw2, gb2 = wgrad_aside(g2, p2, 64, 256)
             gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
             g1 = torch.empty((9 * n, 64), **kw)                               # relu'(conv1) * col2im, one kernel
             _lib.check(L.conv_patches_grad_f64(_ptr(gp2), _ptr(p2), _ptr(g1), n, 64, 3, 3, 2, 2, st), "conv_patches_grad_f64")
             p1 = torch.empty((9 * n, 4), **kw)                                # conv1's patches of the input boards
             _lib.check(L.conv_patches_f64(_ptr(x), _ptr(p1), n, 1, 4, 4, 2, 2, st), "conv_patches_f64")
-            gw1, gb1 = wgrad(g1, p1, 64, 4)
+            gw1, gb1 = wgrad(g1, p1, 64, 4, st)
+            main.wait_stream(side)
         return None, gw1.view(64, 1, 2, 2), gb1, gw2.view(64, 64, 2, 2), gb2, gw3, gb3, gw4, gb4
 
 
