@@ -89,77 +89,89 @@ def _side_stream(device) -> torch.cuda.Stream:
     return _SIDE[key]
 
 
-class _ConvQTrain(torch.autograd.Function):
-    """Q(s) of the conv Q-network with a hand-built backward (train_step, src/dqn_lib.py:146-161).
+def conv_q_forward_saving(x, params):
+    """K6 with saved activations on x [n,16] (float64, contiguous): -> (q [n,4], saved) where saved =
+    (x, patches2 [4n,256], act2 [n,256], act3 [n,64]) is what `conv_q_backward` needs.  No autograd."""
+    n = x.shape[0]
+    dev = _dev(x)
+    _lib.init(dev)
+    kw = dict(dtype=torch.float64, device=x.device)
+    q, p2 = torch.empty((n, 4), **kw), torch.empty((4 * n, 256), **kw)
+    a2, a3 = torch.empty((n, 256), **kw), torch.empty((n, 64), **kw)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qnet_conv_forward_train_f64(_ptr(x), *[_ptr(p) for p in params], _ptr(q), _ptr(p2), _ptr(a2),
+                                                          _ptr(a3), n, _stream(x)), "qnet_conv_forward_train_f64")
+    return q, (x, p2, a2, a3)
 
-    forward: one K6 launch that also stores the three activations the backward needs (the second
-    convolution's im2col input, relu(conv2), relu(fc1)).  backward: per layer the weight / bias gradient
-    kernels of csrc/wgrad_kernels.cu (K7) on those stored matrices, cuBLAS DGEMMs for the input gradients,
-    ATen's threshold_backward for the ReLU masks and one masked col2im.  Same arithmetic as autograd on
-    the nn.Sequential, different summation order (1e-10 relative on the gradients)."""
+
+def conv_q_backward(saved, params, gq, out=None):
+    """Gradients of the eight parameter tensors given gq = d loss / d q [n,4]: per layer the K7 weight /
+    bias gradient kernels on the saved matrices (on a side stream: they are leaves of the dependency chain
+    g4 -> g3 -> g2 -> g1), cuBLAS DGEMMs for the input gradients, ATen's threshold_backward for the ReLU
+    masks and one masked col2im.  `out` (optional): eight contiguous tensors in parameter order that
+    receive the gradients (overwritten, not accumulated) — e.g. the views of a flat gradient buffer."""
+    x, p2, a2, a3 = saved
+    w2, w3, w4 = params[2], params[4], params[6]
+    n = x.shape[0]
+    dev = _dev(x)
+    L = _lib.lib()
+    kw = dict(dtype=torch.float64, device=x.device)
+    main = torch.cuda.current_stream(x.device)
+    side = _side_stream(x.device)
+    st = main.cuda_stream
+    if out is None:
+        out = [torch.empty(p.shape, **kw) for p in params]
+    gw1, gb1, gw2, gb2, gw3, gb3, gw4, gb4 = out
+
+    def wgrad(g, xin, gw, gb, c, k, stream):
+        if c * k <= 1024:
+            scratch = torch.empty(L.layer_wgrad_small_scratch_elems(g.shape[0], c, k), **kw)
+            _lib.check(L.layer_wgrad_small_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], c, k,
+                                               stream), "layer_wgrad_small_f64")
+        else:
+            scratch = torch.empty(L.layer_wgrad64_scratch_elems(g.shape[0], k), **kw)
+            _lib.check(L.layer_wgrad64_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], k, stream),
+                       "layer_wgrad64_f64")
+
+    def wgrad_aside(g, xin, gw, gb, c, k):     # fork here, join at the end; capturable into a CUDA graph
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            wgrad(g, xin, gw, gb, c, k, side.cuda_stream)
+
+    relu_grad = torch.ops.aten.threshold_backward
+    with torch.cuda.device(dev):
+        g4 = gq.contiguous()                                              # [n, 4]
+        wgrad_aside(g4, a3, gw4, gb4, 4, 64)
+        g3 = relu_grad(torch.mm(g4, w4), a3, 0.0)                         # [n, 64]
+        wgrad_aside(g3, a2, gw3, gb3, 64, 256)
+        g2f = relu_grad(torch.mm(g3, w3), a2, 0.0)                        # [n, 256], feature = channel*4 + position
+        g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
+        wgrad_aside(g2, p2, gw2, gb2, 64, 256)
+        gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
+        g1 = torch.empty((9 * n, 64), **kw)                               # relu'(conv1) * col2im, one kernel
+        _lib.check(L.conv_patches_grad_f64(_ptr(gp2), _ptr(p2), _ptr(g1), n, 64, 3, 3, 2, 2, st), "conv_patches_grad_f64")
+        p1 = torch.empty((9 * n, 4), **kw)                                # conv1's patches of the input boards
+        _lib.check(L.conv_patches_f64(_ptr(x), _ptr(p1), n, 1, 4, 4, 2, 2, st), "conv_patches_f64")
+        wgrad(g1, p1, gw1, gb1, 64, 4, st)
+        main.wait_stream(side)
+    return out
+
+
+class _ConvQTrain(torch.autograd.Function):
+    """Q(s) of the conv Q-network with a hand-built backward (train_step, src/dqn_lib.py:146-161):
+    `conv_q_forward_saving` / `conv_q_backward` behind autograd.  Same arithmetic as autograd on the
+    nn.Sequential, different summation order (1e-10 relative on the gradients)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4):
-        n = x.shape[0]
-        dev = _dev(x)
-        _lib.init(dev)
-        kw = dict(dtype=torch.float64, device=x.device)
-        q, p2 = torch.empty((n, 4), **kw), torch.empty((4 * n, 256), **kw)
-        a2, a3 = torch.empty((n, 256), **kw), torch.empty((n, 64), **kw)
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().qnet_conv_forward_train_f64(
-                _ptr(x), *[_ptr(p) for p in (w1, b1, w2, b2, w3, b3, w4, b4)], _ptr(q), _ptr(p2), _ptr(a2), _ptr(a3), n,
-                _stream(x)), "qnet_conv_forward_train_f64")
-        ctx.save_for_backward(x, w2, w3, w4, p2, a2, a3)
+    def forward(ctx, x, *params):
+        q, saved = conv_q_forward_saving(x, params)
+        ctx.save_for_backward(*saved, *params)
         return q
 
     @staticmethod
     def backward(ctx, gq):
-        x, w2, w3, w4, p2, a2, a3 = ctx.saved_tensors
-        n = x.shape[0]
-        dev = _dev(x)
-        L = _lib.lib()
-        kw = dict(dtype=torch.float64, device=x.device)
-        main = torch.cuda.current_stream(x.device)
-        side = _side_stream(x.device)
-        st = main.cuda_stream
-
-        def wgrad(g, xin, c, k, stream):
-            gw, gb = torch.empty((c, k), **kw), torch.empty(c, **kw)
-            if c * k <= 1024:
-                scratch = torch.empty(L.layer_wgrad_small_scratch_elems(g.shape[0], c, k), **kw)
-                _lib.check(L.layer_wgrad_small_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], c, k,
-                                                   stream), "layer_wgrad_small_f64")
-            else:
-                scratch = torch.empty(L.layer_wgrad64_scratch_elems(g.shape[0], k), **kw)
-                _lib.check(L.layer_wgrad64_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], k, stream),
-                           "layer_wgrad64_f64")
-            return gw, gb
-
-        def wgrad_aside(g, xin, c, k):
-            """The weight gradients are leaves of the dependency chain g4 -> g3 -> g2 -> g1: they run on a
-            side stream next to the input-gradient GEMMs (fork here, join at the end; capturable)."""
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                return wgrad(g, xin, c, k, side.cuda_stream)
-
-        relu_grad = torch.ops.aten.threshold_backward
-        with torch.cuda.device(dev):
-            g4 = gq.contiguous()                                              # [n, 4]
-            gw4, gb4 = wgrad_aside(g4, a3, 4, 64)
-            g3 = relu_grad(torch.mm(g4, w4), a3, 0.0)                         # [n, 64]
-            gw3, gb3 = wgrad_aside(g3, a2, 64, 256)
-            g2f = relu_grad(torch.mm(g3, w3), a2, 0.0)                        # [n, 256], feature = channel*4 + position
-            g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
-            gw2, gb2 = wgrad_aside(g2, p2, 64, 256)
-            gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
-            g1 = torch.empty((9 * n, 64), **kw)                               # relu'(conv1) * col2im, one kernel
-            _lib.check(L.conv_patches_grad_f64(_ptr(gp2), _ptr(p2), _ptr(g1), n, 64, 3, 3, 2, 2, st), "conv_patches_grad_f64")
-            p1 = torch.empty((9 * n, 4), **kw)                                # conv1's patches of the input boards
-            _lib.check(L.conv_patches_f64(_ptr(x), _ptr(p1), n, 1, 4, 4, 2, 2, st), "conv_patches_f64")
-            gw1, gb1 = wgrad(g1, p1, 64, 4, st)
-            main.wait_stream(side)
-        return None, gw1.view(64, 1, 2, 2), gb1, gw2.view(64, 64, 2, 2), gb2, gw3, gb3, gw4, gb4
+        t = ctx.saved_tensors
+        return (None, *conv_q_backward(t[:4], t[4:], gq))
 
 
 class TrainableConvQ(nn.Module):
@@ -182,8 +194,23 @@ class TrainableConvQ(nn.Module):
             return FastQNet(self.net)(x.reshape(n, 1, 4, 4)) if FastQNet.supports(self.net) else self.net(x)
         if n == 0 or not (torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters())):
             return self._fused(x2)
+        return _ConvQTrain.apply(x2, *self.params())
+
+    def params(self):
+        """The eight parameter tensors in the order the kernels take them (= nn.Sequential order)."""
         c1, _, c2, _, _, l1, _, l2 = self.net
-        return _ConvQTrain.apply(x2, c1.weight, c1.bias, c2.weight, c2.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+        return (c1.weight, c1.bias, c2.weight, c2.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+
+    @torch.no_grad()
+    def forward_saving(self, x: torch.Tensor):
+        """Q(s) plus the activations `backward_into` needs, outside autograd (DDQNUpdater's direct path)."""
+        return conv_q_forward_saving(x.reshape(x.shape[0], 16), self.params())
+
+    @torch.no_grad()
+    def backward_into(self, saved, gq: torch.Tensor, grads) -> None:
+        """Writes d loss / d parameter into `grads` (eight contiguous tensors in `params()` order),
+        overwriting them — no zeroing and no accumulate kernels."""
+        conv_q_backward(saved, self.params(), gq, out=list(grads))
 
 
 def accelerate_inference(net: nn.Module):

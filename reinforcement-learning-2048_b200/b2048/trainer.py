@@ -14,7 +14,7 @@ import copy
 import torch
 
 from . import ddqn, dist as bdist
-from .qfused import FusedConvQ, accelerate_inference
+from .qfused import FusedConvQ, TrainableConvQ, accelerate_inference
 from .qnet import accelerate
 from .replay import ReplayRing
 
@@ -78,7 +78,11 @@ class DDQNUpdater:
             self.side2.wait_stream(main)
             with torch.cuda.stream(self.side2), torch.no_grad():
                 q_next_online = self._infer(self.i_model, next_states)
-        q_cur = self.f_model(self._shape(states))
+        direct = isinstance(self.f_model, TrainableConvQ)      # conv config: no autograd graph at all
+        if direct:
+            q_cur, saved = self.f_model.forward_saving(states)
+        else:
+            q_cur = self.f_model(self._shape(states))
         main.wait_stream(self.side)
         if self.use_double:
             main.wait_stream(self.side2)
@@ -86,16 +90,23 @@ class DDQNUpdater:
             q_next_target.record_stream(main)
             if q_next_online is not None:
                 q_next_online.record_stream(main)
-        loss, _, _ = ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones, self.gamma,
-                                    self.use_double)
-        self.grads.zero_()
-        loss.backward()
+        if direct:
+            # K3 also emits d loss / d Q(s,.); K7 writes every parameter gradient straight into the flat
+            # buffer (overwrite: no zeroing, no per-parameter accumulate kernels)
+            loss, _, _, grad_q = ddqn.ddqn_target_loss(q_next_online, q_next_target, q_cur, actions, rewards, dones,
+                                                       self.gamma, self.use_double, want_grad=True)
+            self.f_model.backward_into(saved, grad_q, [p.grad for p in self.grads.params])
+        else:
+            loss, _, _ = ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones, self.gamma,
+                                        self.use_double)
+            self.grads.zero_()
+            loss.backward()
         if self.exchange is not None:    # sum over ranks == gradient of the summed loss over the global batch
             self.exchange.allreduce_adam(self.opt)
         else:
             self.grads.allreduce_()
             self.opt.step()
-        self.loss.copy_(loss.detach())
+        self.loss.copy_(loss.detach().reshape(()))
 
     def update(self) -> torch.Tensor:
         """One update; returns the (device) loss tensor of this rank's batch."""
