@@ -1,9 +1,10 @@
-// qnet_kernels.cu — K6: the reference's convolutional Q-network, forward only, as ONE kernel.
+// qnet_kernels.cu — K6: the forward pass of the reference's convolutional Q-network as ONE kernel.
 //
 // Replaces `model(state)` for the conv config (src/configs/double_dqn_conv.py:19-28:
-// Conv2d(1,64,2) ReLU Conv2d(64,64,2) ReLU Flatten Linear(256,64) ReLU Linear(64,4), float64) where no
-// gradient is needed: action selection in epsilon_greedy_policy (src/dqn_lib.py:24-25), greedy play
-// (src/player.py:47) and the two target-side forwards of train_step (src/dqn_lib.py:126-128).
+// Conv2d(1,64,2) ReLU Conv2d(64,64,2) ReLU Flatten Linear(256,64) ReLU Linear(64,4), float64): action
+// selection in epsilon_greedy_policy (src/dqn_lib.py:24-25), greedy play (src/player.py:47), the two
+// target-side forwards of train_step (src/dqn_lib.py:126-128) and — in the SAVE instantiation, which
+// also stores the activations a backward pass needs — Q(s) of train_step itself (:146).
 // Input is either packed boards (exponents as in board.log_scale(), or tiles / max tile as in
 // board.normalized()) or the float64 [n,16] states the replay ring emits; output is Q[n,4].
 //
