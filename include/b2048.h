@@ -214,13 +214,11 @@ int ddqn_target_loss(const double* q_next_online, const double* q_next_target, c
  * consecutive convolutions need no layout round trip.
  *   conv_patches_f64:      x [n*h*w, c] -> cols [n*oh*ow, c*kh*kw], (c,kh,kw) order like conv.weight
  *   conv_patches_grad_f64: d cols -> d x [n*h*w, c] (each input element sums the <= kh*kw patches
- *                          that read it: a gather, deterministic, no atomics).  act_cols (nullable):
- *                          the forward patch matrix of a post-ReLU activation; d x is then also
- *                          masked with (activation > 0), i.e. the gradient of "ReLU, then im2col". */
+ *                          that read it: a gather, deterministic, no atomics) */
 int conv_patches_f64(const double* x, double* cols, int64_t n, int c, int h, int w, int kh, int kw,
                      void* stream);
-int conv_patches_grad_f64(const double* dcols, const double* act_cols, double* dx, int64_t n, int c, int h,
-                          int w, int kh, int kw, void* stream);
+int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
+                          int kw, void* stream);
 
 /* Fused Adam step on one flat float64 parameter buffer (= optimizer.step() of torch.optim.Adam
  * without weight decay / amsgrad, configs/double_dqn_*.py: Adam(lr=1e-2); src/dqn_lib.py:163).
@@ -318,6 +316,15 @@ int layer_wgrad_small_f64(const double* g, const double* x, double* dw, double* 
 int64_t layer_wgrad64_scratch_elems(int64_t rows, int K);
 int layer_wgrad64_f64(const double* g, const double* x, double* dw, double* db, double* scratch, int64_t rows,
                       int K, void* stream);
+
+/* Backward of the conv Q-network's first convolution in one pass (train_step, src/dqn_lib.py:159-161):
+ * given gpatches2 = d loss / d patches2 [4n,256] and the forward patches2 (qnet_conv_forward_train_f64),
+ * col2im, the ReLU mask of conv1 and dW1 [64,1,2,2] / db1 [64] against the boards' cells (states [n,16])
+ * without materialising the conv1 gradient.  Fixed summation order.
+ * scratch: conv1_wgrad_fused_scratch_elems(n) doubles. */
+int64_t conv1_wgrad_fused_scratch_elems(int64_t n);
+int conv1_wgrad_fused_f64(const double* gpatches2, const double* patches2, const double* states, double* dw1,
+                          double* db1, double* scratch, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

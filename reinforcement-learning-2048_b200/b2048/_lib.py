@@ -53,7 +53,7 @@ SIGNATURES = {
                                  ctypes.c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_void_p]),
     "conv_patches_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "conv_patches_grad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "conv_patches_grad_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ddqn_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double,
                                ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
     "p2p_get_ipc_handle": (c_int, [c_void_p, ctypes.c_char_p]),
@@ -68,6 +68,8 @@ SIGNATURES = {
     "layer_wgrad64_scratch_elems": (c_int64, [c_int64, c_int]),
     "layer_wgrad64_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "qnet_conv_forward_train_f64": (c_int, [c_void_p] * 13 + [c_int64, c_void_p]),
+    "conv1_wgrad_fused_scratch_elems": (c_int64, [c_int64]),
+    "conv1_wgrad_fused_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "qnet_conv_forward_f64": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_void_p, c_int64, c_void_p]),
 }
 

@@ -108,7 +108,7 @@ def conv_q_backward(saved, params, gq, out=None):
     """Gradients of the eight parameter tensors given gq = d loss / d q [n,4]: per layer the K7 weight /
     bias gradient kernels on the saved matrices (on a side stream: they are leaves of the dependency chain
     g4 -> g3 -> g2 -> g1), cuBLAS DGEMMs for the input gradients, ATen's threshold_backward for the ReLU
-    masks and one masked col2im.  `out` (optional): eight contiguous tensors in parameter order that
+    masks and one fused kernel for the first convolution.  `out` (optional): eight contiguous tensors in parameter order that
     receive the gradients (overwritten, not accumulated) — e.g. the views of a flat gradient buffer."""
     x, p2, a2, a3 = saved
     w2, w3, w4 = params[2], params[4], params[6]
@@ -148,11 +148,10 @@ def conv_q_backward(saved, params, gq, out=None):
         g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
         wgrad_aside(g2, p2, gw2, gb2, 64, 256)
         gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
-        g1 = torch.empty((9 * n, 64), **kw)                               # relu'(conv1) * col2im, one kernel
-        _lib.check(L.conv_patches_grad_f64(_ptr(gp2), _ptr(p2), _ptr(g1), n, 64, 3, 3, 2, 2, st), "conv_patches_grad_f64")
-        p1 = torch.empty((9 * n, 4), **kw)                                # conv1's patches of the input boards
-        _lib.check(L.conv_patches_f64(_ptr(x), _ptr(p1), n, 1, 4, 4, 2, 2, st), "conv_patches_f64")
-        wgrad(g1, p1, gw1, gb1, 64, 4, st)
+        # col2im, relu'(conv1) and dW1 / db1 against the boards' cells in one pass (no conv1 gradient tensor)
+        scratch = torch.empty(L.conv1_wgrad_fused_scratch_elems(n), **kw)
+        _lib.check(L.conv1_wgrad_fused_f64(_ptr(gp2), _ptr(p2), _ptr(x), _ptr(gw1), _ptr(gb1), _ptr(scratch), n, st),
+                   "conv1_wgrad_fused_f64")
         main.wait_stream(side)
     return out
 

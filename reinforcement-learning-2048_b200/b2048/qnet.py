@@ -44,7 +44,7 @@ class _Patches(torch.autograd.Function):
         dcols = dcols.contiguous()
         dx = torch.empty((n * h * w, c), dtype=dcols.dtype, device=dcols.device)
         with torch.cuda.device(dcols.device):
-            _lib.check(_lib.lib().conv_patches_grad_f64(_ptr(dcols), None, _ptr(dx), n, c, h, w, kh, kw, _stream(dcols)),
+            _lib.check(_lib.lib().conv_patches_grad_f64(_ptr(dcols), _ptr(dx), n, c, h, w, kh, kw, _stream(dcols)),
                        "conv_patches_grad_f64")
         return dx, None, None, None, None, None, None
 

@@ -116,13 +116,9 @@ __global__ void patches_kernel(const double* __restrict__ x, double* __restrict_
 
 // dx[(b*h + y)*w + x][ci] = sum over (ky,kx) with 0 <= y-ky < oh, 0 <= x-kx < ow of
 // dcols[patch (y-ky, x-kx)][(ci*kh + ky)*kw + kx]: a gather per input element (deterministic).
-// act_cols (nullable): the forward patch matrix of a post-ReLU activation; every entry that reads input
-// element (pixel, ci) holds that element's value, so the ReLU mask (value > 0) comes from any one of them
-// and the gradient of "ReLU then im2col" is produced in one pass.
 template <typename I>
-__global__ void patches_grad_kernel(const double* __restrict__ dcols, const double* __restrict__ act_cols,
-                                    double* __restrict__ dx, I total, int c, int h, int w, int kh, int kw, int oh,
-                                    int ow) {
+__global__ void patches_grad_kernel(const double* __restrict__ dcols, double* __restrict__ dx, I total, int c,
+                                    int h, int w, int kh, int kw, int oh, int ow) {
   const I i = (I)blockIdx.x * blockDim.x + threadIdx.x;   // = ((b*h + y)*w + x)*c + ci
   if (i >= total) return;
   const I pix = i / (I)c;
@@ -133,22 +129,16 @@ __global__ void patches_grad_kernel(const double* __restrict__ dcols, const doub
   const I b = t / (I)h;
   const I K = (I)c * kh * kw;
   double acc = 0.0;
-  bool alive = true, checked = act_cols == nullptr;
   for (int ky = 0; ky < kh; ++ky) {
     const int oy = yy - ky;
     if (oy < 0 || oy >= oh) continue;
     for (int kx = 0; kx < kw; ++kx) {
       const int ox = xx - kx;
       if (ox < 0 || ox >= ow) continue;
-      const I at = ((b * oh + oy) * ow + ox) * K + (I)((ci * kh + ky) * kw + kx);
-      acc += dcols[at];
-      if (!checked) {          // every contributing entry holds the same activation: look at the first only
-        checked = true;
-        alive = act_cols[at] > 0.0;
-      }
+      acc += dcols[((b * oh + oy) * ow + ox) * K + (I)((ci * kh + ky) * kw + kx)];
     }
   }
-  dx[i] = alive ? acc : 0.0;
+  dx[i] = acc;
 }
 
 __global__ void adam_kernel(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,
@@ -264,8 +254,8 @@ extern "C" int conv_patches_f64(const double* x, double* cols, int64_t n, int c,
   return (int)cudaGetLastError();
 }
 
-extern "C" int conv_patches_grad_f64(const double* dcols, const double* act_cols, double* dx, int64_t n, int c, int h,
-                                     int w, int kh, int kw, void* stream) {
+extern "C" int conv_patches_grad_f64(const double* dcols, double* dx, int64_t n, int c, int h, int w, int kh,
+                                     int kw, void* stream) {
   if (!dcols || !dx || !patches_args_ok(n, c, h, w, kh, kw)) return B2048_EINVAL;
   int err = 0;
   if (!current_ctx(&err)) return err;
@@ -274,9 +264,9 @@ extern "C" int conv_patches_grad_f64(const double* dcols, const double* act_cols
   const unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n * oh * ow * c * kh * kw < (1ll << 31) && total < (1ll << 31))
-    patches_grad_kernel<uint32_t><<<grid, 256, 0, st>>>(dcols, act_cols, dx, (uint32_t)total, c, h, w, kh, kw, oh, ow);
+    patches_grad_kernel<uint32_t><<<grid, 256, 0, st>>>(dcols, dx, (uint32_t)total, c, h, w, kh, kw, oh, ow);
   else
-    patches_grad_kernel<int64_t><<<grid, 256, 0, st>>>(dcols, act_cols, dx, total, c, h, w, kh, kw, oh, ow);
+    patches_grad_kernel<int64_t><<<grid, 256, 0, st>>>(dcols, dx, total, c, h, w, kh, kw, oh, ow);
   return (int)cudaGetLastError();
 }
 

@@ -219,6 +219,85 @@ int64_t wt_blocks(int64_t rows, int sms) {
   return b < 1 ? 1 : b;
 }
 
+// ---- first convolution of the conv Q-network: col2im + ReLU mask + weight / bias gradient in one pass ----
+// Backward of "conv1 -> ReLU -> im2col" given gp2 = d loss / d patches2 [4n, 256] (row = board*4 + conv2
+// position, column = channel*4 + tap) and the forward patches2 (the ReLU mask: every entry that reads a
+// conv1 output holds its value).  Unfused this is a col2im kernel that materialises g1 [9n, 64], a patch
+// gather of the boards and the small weight-gradient kernel: 23 + 4 + 17 us and 2 x 23 MB of traffic for g1.
+// Here a thread owns (board, channel): the 16 gp2 / patches2 entries of that pair are four 32-byte rows,
+// the nine conv1 outputs' gradients are sums of up to four of them, and dW1[c][tap] / db1[c] accumulate
+// against the board's cells in registers.  64 channels x 4 board lanes per block; per-block partial sums,
+// then wgrad_reduce_kernel (fixed order).
+__global__ void __launch_bounds__(256)
+    conv1_wgrad_fused_kernel(const double* __restrict__ gp2, const double* __restrict__ p2,
+                             const double* __restrict__ x, double* __restrict__ partials, int64_t n,
+                             int64_t boards_per_block) {
+  __shared__ double sm[3][5][64];
+  const int ci = threadIdx.x & 63, bl = threadIdx.x >> 6;
+  const int64_t b0 = (int64_t)blockIdx.x * boards_per_block;
+  const int64_t b1 = b0 + boards_per_block < n ? b0 + boards_per_block : n;
+  double dw[4] = {0.0, 0.0, 0.0, 0.0}, db = 0.0;
+  for (int64_t b = b0 + bl; b < b1; b += 4) {
+    double g[4][4], a[4][4], xb[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2* gr = reinterpret_cast<const double2*>(gp2 + (b * 4 + q) * 256 + ci * 4);
+      const double2* ar = reinterpret_cast<const double2*>(p2 + (b * 4 + q) * 256 + ci * 4);
+      const double2 g0 = gr[0], g1 = gr[1], a0 = ar[0], a1 = ar[1];
+      g[q][0] = g0.x; g[q][1] = g0.y; g[q][2] = g1.x; g[q][3] = g1.y;
+      a[q][0] = a0.x; a[q][1] = a0.y; a[q][2] = a1.x; a[q][3] = a1.y;
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) xb[c] = x[b * 16 + c];
+#pragma unroll
+    for (int y = 0; y < 3; ++y)
+#pragma unroll
+      for (int xx = 0; xx < 3; ++xx) {
+        // conv1 output (y, xx) is read by conv2 position (y-ky, xx-kx) through tap (ky, kx)
+        double s = 0.0, act = 0.0;
+        bool seen = false;
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 2; ++kx) {
+            const int oy = y - ky, ox = xx - kx;
+            if (oy < 0 || oy > 1 || ox < 0 || ox > 1) continue;
+            s += g[oy * 2 + ox][ky * 2 + kx];
+            if (!seen) { act = a[oy * 2 + ox][ky * 2 + kx]; seen = true; }
+          }
+        if (!(act > 0.0)) s = 0.0;
+        db += s;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dw[k] = fma(s, xb[(y + (k >> 1)) * 4 + xx + (k & 1)], dw[k]);
+      }
+  }
+  // combine the four board lanes in lane order, then one partial record per block: [64*4 dW | 64 db]
+  if (bl > 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sm[bl - 1][k][ci] = dw[k];
+    sm[bl - 1][4][ci] = db;
+  }
+  __syncthreads();
+  if (bl == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dw[k] += sm[j][k][ci];
+      db += sm[j][4][ci];
+    }
+    double* mine = partials + (int64_t)blockIdx.x * 320;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mine[ci * 4 + k] = dw[k];
+    mine[256 + ci] = db;
+  }
+}
+
+int64_t c1_blocks(int64_t n, int sms) {
+  int64_t b = (n + 15) / 16;          // at least 16 boards (4 per lane) per block
+  if (b > 2 * (int64_t)sms) b = 2 * sms;
+  return b < 1 ? 1 : b;
+}
+
 }  // namespace
 }  // namespace b2048
 
@@ -282,3 +361,28 @@ cudaError_t wgrad_kernels_configure() {
   return cudaFuncSetAttribute(wgrad_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES);
 }
 }  // namespace b2048
+
+extern "C" int64_t conv1_wgrad_fused_scratch_elems(int64_t n) {
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx || n <= 0) return 0;
+  return c1_blocks(n, ctx->sm_count) * 320;
+}
+
+extern "C" int conv1_wgrad_fused_f64(const double* gpatches2, const double* patches2, const double* states, double* dw1,
+                                     double* db1, double* scratch, int64_t n, void* stream) {
+  if (n <= 0 || !gpatches2 || !patches2 || !states || !dw1 || !db1 || !scratch ||
+      ((reinterpret_cast<uintptr_t>(gpatches2) | reinterpret_cast<uintptr_t>(patches2)) & 15u))
+    return B2048_EINVAL;
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  const int64_t blocks = c1_blocks(n, ctx->sm_count);
+  const int64_t bpb = ((n + blocks - 1) / blocks + 3) / 4 * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  conv1_wgrad_fused_kernel<<<(unsigned)blocks, 256, 0, st>>>(gpatches2, patches2, states, scratch, n, bpb);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  wgrad_reduce_kernel<<<(320 + 31) / 32, 256, 0, st>>>(scratch, dw1, db1, 256, 64, (int)blocks);
+  return (int)cudaGetLastError();
+}

@@ -238,6 +238,51 @@ def test_dmma_weight_gradient_kernel(cuda, rows, k):
         assert L.layer_wgrad64_f64(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), rows, 48, _stream(g)) == -2
 
 
+@pytest.mark.parametrize("n", [1, 5, 16, 17, 5000, 6001])
+def test_fused_conv1_backward_kernel(cuda, n):
+    """conv1_wgrad_fused_f64 = col2im + ReLU mask + (dW1, db1) in one pass, against the same thing spelled
+    out with torch ops on the unfused tensors; run-to-run bit-identical."""
+    from b2048 import _lib
+    from b2048.env import _ptr, _stream
+    _lib.init(torch.device(cuda).index or 0)
+    L = _lib.lib()
+    torch.manual_seed(n)
+    x = torch.randint(0, 12, (n, 16), device=cuda).double()
+    w1 = torch.randn(64, 4, dtype=torch.float64, device=cuda)
+    b1 = torch.randn(64, dtype=torch.float64, device=cuda)
+    # forward pieces: conv1 patches [9n,4] -> out1 [n,3,3,64] -> patches2 [4n,256] in (c, ky, kx) column order
+    xi = x.view(n, 4, 4)
+    p1 = torch.stack([xi[:, y + ky, xx + kx] for y in range(3) for xx in range(3) for ky in range(2) for kx in range(2)], 1).view(n * 9, 4)
+    out1 = torch.relu(p1 @ w1.t() + b1).view(n, 3, 3, 64)
+    p2 = torch.stack([out1[:, oy + ky, ox + kx, :] for oy in range(2) for ox in range(2) for ky in range(2) for kx in range(2)], 1)
+    p2 = p2.view(n, 4, 4, 64).permute(0, 1, 3, 2).reshape(4 * n, 256).contiguous()        # [.., c*4 + tap]
+    gp2 = torch.randn(4 * n, 256, dtype=torch.float64, device=cuda)
+    # reference: col2im of gp2, mask by out1 > 0, then dW1 = g1^T p1, db1 = column sums
+    g1 = torch.zeros(n, 3, 3, 64, dtype=torch.float64, device=cuda)
+    gv = gp2.view(n, 2, 2, 64, 2, 2)
+    for oy in range(2):
+        for ox in range(2):
+            for ky in range(2):
+                for kx in range(2):
+                    g1[:, oy + ky, ox + kx, :] += gv[:, oy, ox, :, ky, kx]
+    g1 = (g1 * (out1 > 0)).view(9 * n, 64)
+    want_w, want_b = g1.t() @ p1, g1.sum(0)
+    scratch = torch.empty(L.conv1_wgrad_fused_scratch_elems(n), dtype=torch.float64, device=cuda)
+
+    def run():
+        dw = torch.full((64, 4), float("nan"), dtype=torch.float64, device=cuda)
+        db = torch.full((64,), float("nan"), dtype=torch.float64, device=cuda)
+        with torch.cuda.device(cuda):
+            assert L.conv1_wgrad_fused_f64(_ptr(gp2), _ptr(p2), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), n, _stream(x)) == 0
+        return dw, db
+
+    dw, db = run()
+    dw2, db2 = run()
+    assert float((dw - want_w).abs().max()) <= 1e-11 * max(1.0, float(want_w.abs().max()))
+    assert float((db - want_b).abs().max()) <= 1e-11 * max(1.0, float(want_b.abs().max()))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
 def test_batched_player_baselines(cuda):
     """The reference's player.py policies at scale: random-legal and up-left baselines."""
     from b2048.player import BatchedPlayer
