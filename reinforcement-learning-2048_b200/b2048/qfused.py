@@ -133,21 +133,34 @@ def conv_q_backward(saved, params, gq, out=None):
             _lib.check(L.layer_wgrad64_f64(_ptr(g), _ptr(xin), _ptr(gw), _ptr(gb), _ptr(scratch), g.shape[0], k, stream),
                        "layer_wgrad64_f64")
 
-    def wgrad_aside(g, xin, gw, gb, c, k):     # fork here, join at the end; capturable into a CUDA graph
-        side.wait_stream(main)
+    def ready():                                # marks "g is complete" on the main stream
+        ev = torch.cuda.Event()
+        ev.record(main)
+        return ev
+
+    def wgrad_aside(ev, g, xin, gw, gb, c, k):  # fork at `ev`, join at the end; capturable into a CUDA graph
+        side.wait_event(ev)
         with torch.cuda.stream(side):
             wgrad(g, xin, gw, gb, c, k, side.cuda_stream)
 
+    # Per layer: the input-gradient GEMM (critical path) is launched first, the weight-gradient kernel of
+    # the same layer second, on the side stream, waiting only for g: it fills in behind the GEMM's CTAs
+    # instead of taking the SMs' shared memory ahead of it.
     relu_grad = torch.ops.aten.threshold_backward
     with torch.cuda.device(dev):
         g4 = gq.contiguous()                                              # [n, 4]
-        wgrad_aside(g4, a3, gw4, gb4, 4, 64)
-        g3 = relu_grad(torch.mm(g4, w4), a3, 0.0)                         # [n, 64]
-        wgrad_aside(g3, a2, gw3, gb3, 64, 256)
-        g2f = relu_grad(torch.mm(g3, w3), a2, 0.0)                        # [n, 256], feature = channel*4 + position
+        ev = ready()
+        t3 = torch.mm(g4, w4)
+        wgrad_aside(ev, g4, a3, gw4, gb4, 4, 64)
+        g3 = relu_grad(t3, a3, 0.0)                                       # [n, 64]
+        ev = ready()
+        t2 = torch.mm(g3, w3)
+        wgrad_aside(ev, g3, a2, gw3, gb3, 64, 256)
+        g2f = relu_grad(t2, a2, 0.0)                                      # [n, 256], feature = channel*4 + position
         g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
-        wgrad_aside(g2, p2, gw2, gb2, 64, 256)
+        ev = ready()
         gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
+        wgrad_aside(ev, g2, p2, gw2, gb2, 64, 256)
         # col2im, relu'(conv1) and dW1 / db1 against the boards' cells in one pass (no conv1 gradient tensor)
         scratch = torch.empty(L.conv1_wgrad_fused_scratch_elems(n), **kw)
         _lib.check(L.conv1_wgrad_fused_f64(_ptr(gp2), _ptr(p2), _ptr(x), _ptr(gw1), _ptr(gb1), _ptr(scratch), n, st),
