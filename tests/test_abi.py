@@ -73,3 +73,12 @@ def test_compute_fails_loudly_without_gpu():
     p = ctypes.c_void_p(z.ctypes.data)
     rc = _lib.lib().b2048_legal_mask(p, p, 4, None)
     assert rc in (-1, -3)
+
+
+def test_docs_state_the_current_entry_point_count():
+    """README / DESIGN / INTEGRATION quote the number of C-ABI entry points; keep them honest."""
+    n = len(declared_functions())
+    for name in ("README.md", "DESIGN.md", "INTEGRATION.md"):
+        text = open(os.path.join(ROOT, name)).read()
+        found = [int(m) for m in re.findall(r"(\d+) (?:`extern \"C\"` )?entry points", text)]
+        assert found and all(f == n for f in found), (name, found, n)
