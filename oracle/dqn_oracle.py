@@ -79,3 +79,23 @@ def ddqn_target_loss(q_next_online, q_next_target, q_cur, actions, rewards, done
     grad = np.zeros_like(qc)
     grad[rows, a] = 2.0 * diff
     return target, q_sa, loss, grad
+
+
+# ---- the conv Q-network's forward (src/configs/double_dqn_conv.py:19-28) --------------------------------
+
+def conv_q_forward(states: np.ndarray, w1, b1, w2, b2, w3, b3, w4, b4) -> np.ndarray:
+    """Q-values of Conv2d(1,64,2) ReLU Conv2d(64,64,2) ReLU Flatten Linear(256,64) ReLU Linear(64,4) in
+    float64 numpy: states [n,16] (exponents) -> [n,4].  Cross-correlation with valid padding, exactly as
+    torch.nn.Conv2d; nn.Flatten order is (channel, y, x).  Checked against the Q tensors the reference's
+    own train_step produced (tests/golden/dqn_conv.npz)."""
+    n = states.shape[0]
+    x = states.reshape(n, 4, 4)
+    # conv1: out1[n, c, y, x] = b1[c] + sum_{ky,kx} x[n, y+ky, x+kx] * w1[c, 0, ky, kx]
+    p1 = np.stack([x[:, ky:ky + 3, kx:kx + 3] for ky in range(2) for kx in range(2)], axis=-1)      # [n,3,3,4]
+    out1 = np.maximum(p1 @ w1.reshape(64, 4).T + b1, 0.0)                                           # [n,3,3,64]
+    # conv2: out2[n, c2, y, x] = b2[c2] + sum_{c1,ky,kx} out1[n, y+ky, x+kx, c1] * w2[c2, c1, ky, kx]
+    p2 = np.stack([out1[:, ky:ky + 2, kx:kx + 2, :] for ky in range(2) for kx in range(2)], axis=-1)  # [n,2,2,64,4]
+    out2 = np.maximum(p2.reshape(n, 2, 2, 256) @ w2.reshape(64, 256).T + b2, 0.0)                   # [n,2,2,64]
+    flat = out2.transpose(0, 3, 1, 2).reshape(n, 256)                                               # (c, y, x)
+    h = np.maximum(flat @ w3.T + b3, 0.0)
+    return h @ w4.T + b4

@@ -220,6 +220,9 @@ def test_fused_conv_forward_sizes_and_scalings(cuda, n):
             tol = 1e-9 * float(want.abs().max())
             assert float((got - want).abs().max()) <= tol, (scaling, float((got - want).abs().max()), tol)
             assert float((fq(x.contiguous()) - want).abs().max()) <= tol
+    if n <= 5000:                                         # and against the numpy oracle (pinned to the reference's Q tensors)
+        want = do.conv_q_forward(x_log.reshape(n, 16).cpu().numpy(), *[p.detach().cpu().numpy() for p in net.parameters()])
+        assert np.abs(fq.forward_boards(boards).cpu().numpy() - want).max() <= 1e-9 * np.abs(want).max()
     # the kernel reads the module's parameters at call time: an in-place weight change is seen
     with torch.no_grad():
         net[7].bias.add_(1.0)

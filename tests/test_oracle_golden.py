@@ -164,6 +164,18 @@ def test_ddqn_target_loss_matches_reference(g, name, tag):
     assert (np.abs(g64 - t) > 1e-9 * np.abs(t)).any()
 
 
+def test_conv_q_forward_matches_reference_q_values(g):
+    """The numpy restatement of the conv Q-network against the Q tensors of the reference's train_step
+    (its own weights, its own sampled batch): pins the oracle the GPU kernel K6 is compared with."""
+    d = g["dqn_conv"]
+    on = [d[f"w_{k}"] for k in ("0.weight", "0.bias", "2.weight", "2.bias", "5.weight", "5.bias", "7.weight", "7.bias")]
+    tg = [d[f"tw_{k}"] for k in ("0.weight", "0.bias", "2.weight", "2.bias", "5.weight", "5.bias", "7.weight", "7.bias")]
+    for got, want in ((do.conv_q_forward(d["states"], *on), d["q_cur"]),
+                      (do.conv_q_forward(d["next_states"], *on), d["q_next_online"]),
+                      (do.conv_q_forward(d["next_states"], *tg), d["q_next_target"])):
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.abs(want).max())
+
+
 def test_egreedy_matches_reference(g):
     e = g["egreedy"]
     acts, mq = do.egreedy_batch(e["q"], e["legal"], np.full(len(e["q"]), 0x80, np.uint8))
