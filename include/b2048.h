@@ -14,6 +14,9 @@
  *   - return value is an `int`: 0 = ok, >0 = a `cudaError_t`, <0 = a B2048_E* code below;
  *   - device-pointer calls never allocate, never synchronise and never throw after
  *     `b2048_init(device)`; they are safe to capture in a CUDA graph;
+ *   - device-pointer calls are re-entrant: every buffer a launch touches is passed by the caller (the
+ *     only library-owned device state is the read-only row table), so any number of calls may be in
+ *     flight on different streams / host threads of one device.  `*_host` calls serialise per device;
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  *
  * Packed board format ("u64 board"): 16 tile exponents of 4 bits each; cell (row r, column c)
@@ -67,8 +70,8 @@ extern "C" {
 /* ---- lifetime ------------------------------------------------------------------------------ */
 
 /* Build the 65536-entry row table (canonical left slide+merge, = src/board.py:92-126 for every
- * row of 4-bit exponents) and upload it to `device`; allocate the small reduction scratch used
- * by ddqn_target_loss.  Idempotent, thread-safe.  Must precede every other call on `device`. */
+ * row of 4-bit exponents) and upload it to `device`.  Idempotent, thread-safe.  Must precede every
+ * other call on `device`. */
 int b2048_init(int device);
 int b2048_shutdown(int device);
 int b2048_abi_version(void);
@@ -202,7 +205,9 @@ int replay_sample(const b2048_ring* ring, int64_t B, uint64_t seed, uint64_t ctr
  * (use_double != 0) or ... * max_j q_next_target[i,j] (use_double == 0; q_next_online may be NULL);
  * q_sa[i] = q_cur[i, actions[i]]; loss[0] = sum_i (q_sa[i]-target[i])^2 (deterministic order);
  * grad_q_cur (nullable) [B,4] = d loss / d q_cur = 2 (q_sa - target) at column actions[i], else 0.
- * gamma is deliberately a float: the reference rounds it to float32. */
+ * gamma is deliberately a float: the reference rounds it to float32.
+ * One launch = one thread-block cluster whose partial sums meet through distributed shared memory: no
+ * library-owned scratch, so concurrent calls on different streams cannot interfere. */
 int ddqn_target_loss(const double* q_next_online, const double* q_next_target, const double* q_cur,
                      const int64_t* actions, const int64_t* rewards, const int64_t* dones,
                      float gamma_f32, int use_double, double* target, double* q_sa, double* loss,
@@ -240,7 +245,9 @@ int ddqn_adam_step(double* params, const double* grads, double* exp_avg, double*
  *   peer_flags : device array [world] of pointers to every rank's flag block (uint64[2*world],
  *                zero-initialised); my block is peer_flags[rank]
  *   sync_state : device uint64[4], zero-initialised: {epoch, blocks-done counter, error, -}
- * Waits are bounded (~1 s); on timeout sync_state[2] is set to 1 and the kernel returns. */
+ * Waits are bounded (30 s of wall clock); when one expires sync_state[2] is set to 1 (sticky) and the
+ * kernel returns WITHOUT updating params / exp_avg / exp_avg_sq / step_counter, so a lost peer can never
+ * make this replica apply a partial sum; the caller must poll sync_state[2] and treat it as fatal. */
 /* Map a peer's cudaMalloc allocation into this process for access from the CURRENT device
  * (cudaIpcOpenMemHandle with lazy peer access; no context is created on the peer's device).
  * `handle64` is the 64-byte cudaIpcMemHandle_t of the allocation; *out is its base address. */

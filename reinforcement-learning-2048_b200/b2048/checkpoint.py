@@ -27,6 +27,7 @@ _ENV_TENSORS = ("boards", "ep_score", "ep_moves", "ep_qsum", "totals", "qmean_su
 
 
 def save(path: str, updater=None, vector_env=None, ring=None, extra: dict | None = None) -> None:
+    """`extra`: primitives, lists, dicts and tensors only (load() uses torch.load(weights_only=True))."""
     ck = {"format": "b2048-checkpoint-1", "extra": extra or {}}
     if updater is not None:
         ck["model"] = updater.model.state_dict()
@@ -43,7 +44,9 @@ def save(path: str, updater=None, vector_env=None, ring=None, extra: dict | None
 
 
 def load(path: str, updater=None, vector_env=None, ring=None) -> dict:
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    # weights_only: a checkpoint holds tensors, ints, floats, strings, lists and dicts only, so nothing
+    # from an untrusted file is ever unpickled into code (`extra` must stay primitives / tensors)
+    ck = torch.load(path, map_location="cpu", weights_only=True)
     if ck.get("format") != "b2048-checkpoint-1":
         raise ValueError("not a b2048 checkpoint")
     if updater is not None:

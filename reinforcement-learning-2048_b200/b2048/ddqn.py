@@ -110,7 +110,7 @@ class FusedAdam:
 
     def state_dict(self) -> dict:
         return {"exp_avg": self.exp_avg.cpu(), "exp_avg_sq": self.exp_avg_sq.cpu(), "step": self.step_count.cpu(),
-                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+                "lr": self.lr, "betas": list(self.betas), "eps": self.eps}
 
     def load_state_dict(self, st: dict) -> None:
         self.exp_avg.copy_(st["exp_avg"]); self.exp_avg_sq.copy_(st["exp_avg_sq"]); self.step_count.copy_(st["step"])

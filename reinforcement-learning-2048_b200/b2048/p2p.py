@@ -76,3 +76,10 @@ class PeerGradExchange:
     def timed_out(self) -> bool:
         """True if a bounded wait inside the kernel expired (a peer never arrived); synchronises."""
         return bool(self.sync[2].item())
+
+    def check(self) -> None:
+        """Raise if an exchange gave up waiting for a peer (the kernel then skipped the update, so this
+        rank's replica is intact but behind).  The trainers call this wherever they read a scalar back."""
+        if self.timed_out():
+            raise RuntimeError(f"rank {self.rank}: NVLink gradient exchange timed out waiting for a peer; "
+                               "the update was skipped and the replicas are no longer in step")

@@ -119,17 +119,38 @@ class DDQNUpdater:
         self.updates += 1
         return self.loss
 
+    def _trainable_state(self):
+        """Everything one `_update_eager()` changes: weights, Adam moments and step, the ring's
+        sample counter, the reported loss."""
+        return (self.params.flat, self.opt.exp_avg, self.opt.exp_avg_sq, self.opt.step_count,
+                self.ring.head_size, self.loss)
+
     def _capture(self):
+        """Warm-up (allocator, cuBLAS plans) + graph capture, WITHOUT side effects: the three warm-up
+        updates are real ones, so the state they touch is saved before and put back after — the first
+        `update()` in graph mode then applies exactly one optimizer step, and a resumed run continues
+        bit-identically (with several ranks every rank runs the same warm-up exchanges, so the
+        replicas stay in step)."""
+        saved = [t.clone() for t in self._trainable_state()]
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            for _ in range(3):           # warm-up on a side stream (allocator, cuBLAS plans)
+            for _ in range(3):
                 self._update_eager()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._update_eager()
+            self._update_eager()                 # capture only records; nothing executes
+        with torch.no_grad():
+            for t, v in zip(self._trainable_state(), saved):
+                t.copy_(v)
+        torch.cuda.synchronize(self.device)
+
+    def check(self) -> None:
+        """Surface a failed gradient exchange (synchronises; call where a scalar is read back anyway)."""
+        if self.exchange is not None:
+            self.exchange.check()
 
     def sync_target(self) -> None:
         """target <- online (the reference's load_state_dict(deepcopy(...)), src/dqn_lib.py:227-228);

@@ -41,8 +41,6 @@ enum : uint32_t {
 
 struct DeviceCtx {
   uint32_t* lut = nullptr;       // [65536] row table + [LUT_SMEM_ROWS] swizzled copy for shared memory
-  double* partials = nullptr;    // [MAX_PARTIALS] loss partial sums
-  unsigned int* ticket = nullptr;// last-block-done counter
   int sm_count = 0;
   int max_smem_optin = 0;
   bool ready = false;
@@ -53,7 +51,6 @@ struct DeviceCtx {
   cudaEvent_t ws_events[3] = {nullptr, nullptr, nullptr};
 };
 constexpr int MAX_DEVICES = 16;
-constexpr int MAX_PARTIALS = 1024;
 
 // defined in host_api.cu
 DeviceCtx* current_ctx(int* err);
@@ -362,6 +359,38 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;
+}
+// 256-bit accesses (sm_100: LDG.E.256 / STG.E.256): one full 32-byte sector per lane and instruction.
+// Two 128-bit accesses per lane to the halves of one sector make every warp instruction touch 32 sectors
+// for 512 B of payload, and with L1::no_allocate the second one re-fetches all of them from L2
+// (profiles/ubench/stream5.cu: 0.309 -> 0.27 ms for K1's five streams with no arithmetic at all).
+#ifndef B2048_V_LDMODE
+#define B2048_V_LDMODE 0
+#endif
+#ifndef B2048_V_STMODE
+#define B2048_V_STMODE 0
+#endif
+__device__ __forceinline__ void ld_stream_v8(const void* p, uint4& a, uint4& b) {
+#if B2048_V_LDMODE == 0
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif B2048_V_LDMODE == 1
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+  asm volatile("ld.global.cs.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_stream_v8(void* p, uint4 a, uint4 b) {
+#if B2048_V_STMODE == 0
+  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#elif B2048_V_STMODE == 1
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#else
+  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#endif
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
 }
 __device__ __forceinline__ uint2 ld_stream_v2(const void* p) {
   uint2 v;

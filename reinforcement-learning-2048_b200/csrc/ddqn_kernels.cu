@@ -11,10 +11,31 @@
 namespace b2048 {
 namespace {
 
-constexpr int K3_THREADS = 256;
+// One thread-block cluster (8 CTAs x 512 threads, one per SM) handles the whole batch: per-CTA partial
+// sums meet in CTA 0 through distributed shared memory, so the launch needs NO scratch in global memory
+// and is re-entrant — any number of calls may be in flight on different streams of one device
+// (include/b2048.h).  The order of every addition is fixed: bit-reproducible losses.
+constexpr int K3_THREADS = 512;
+constexpr int K3_CLUSTER = 8;
 
-__device__ __forceinline__ double block_sum_256(double v, double* sh) {
-  // fixed-order tree: warp shuffle, then 8 warp partials added in order by thread 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_smem_ptr, uint32_t cta) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  // fixed-order tree: warp shuffle, then the warp partials added in order by thread 0
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -33,10 +54,9 @@ __global__ void __launch_bounds__(K3_THREADS)
                             const int64_t* __restrict__ rewards, const int64_t* __restrict__ dones,
                             float gamma, int use_double, double* __restrict__ target,
                             double* __restrict__ q_sa, double* __restrict__ loss,
-                            double* __restrict__ grad, int64_t B, double* __restrict__ partials,
-                            unsigned int* __restrict__ ticket) {
+                            double* __restrict__ grad, int64_t B) {
   __shared__ double sh[K3_THREADS / 32];
-  __shared__ bool is_last;
+  __shared__ double cta_sum;
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * K3_THREADS + threadIdx.x; i < B;
        i += (int64_t)gridDim.x * K3_THREADS) {
@@ -75,20 +95,15 @@ __global__ void __launch_bounds__(K3_THREADS)
     }
     acc = __dadd_rn(acc, __dmul_rn(diff, diff));
   }
-  const double bs = block_sum_256(acc, sh);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = bs;
-    __threadfence();
-    const unsigned int old = atomicInc(ticket, gridDim.x - 1);  // wraps back to 0 for the next launch
-    is_last = (old == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
+  const double bs = block_sum(acc, sh);
+  if (threadIdx.x == 0) cta_sum = bs;
+  cluster_sync_all();                       // every CTA's partial is visible cluster-wide
+  if (cluster_ctarank() == 0 && threadIdx.x == 0) {
     double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s = __dadd_rn(s, partials[b]);
+    for (uint32_t c = 0; c < (uint32_t)K3_CLUSTER; ++c) s = __dadd_rn(s, ld_dsmem_f64(&cta_sum, c));
     loss[0] = s;
   }
+  cluster_sync_all();                       // peers keep their shared memory alive until CTA 0 has read it
 }
 
 // Activations are row matrices [b*h*w, c] (what a GEMM over patches produces; for c = 1 the same bytes as
@@ -224,14 +239,22 @@ extern "C" int ddqn_target_loss(const double* q_next_online, const double* q_nex
     return B2048_EINVAL;
   if (use_double && !q_next_online) return B2048_EINVAL;
   int err = 0;
-  DeviceCtx* ctx = current_ctx(&err);
-  if (!ctx) return err;
-  int64_t blocks = (B + K3_THREADS - 1) / K3_THREADS;
-  if (blocks > MAX_PARTIALS) blocks = MAX_PARTIALS;
-  ddqn_target_loss_kernel<<<(unsigned)blocks, K3_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      q_next_online, q_next_target, q_cur, actions, rewards, dones, gamma_f32, use_double, target,
-      q_sa, loss, grad_q_cur, B, ctx->partials, ctx->ticket);
-  return (int)cudaGetLastError();
+  if (!current_ctx(&err)) return err;
+  // one cluster of K3_CLUSTER CTAs, whatever B is (grid-stride inside): no global scratch, re-entrant
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(K3_CLUSTER, 1, 1);
+  cfg.blockDim = dim3(K3_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = K3_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, ddqn_target_loss_kernel, q_next_online, q_next_target, q_cur, actions,
+                                 rewards, dones, gamma_f32, use_double, target, q_sa, loss, grad_q_cur, B);
 }
 
 static int patches_args_ok(int64_t n, int c, int h, int w, int kh, int kw) {

@@ -73,6 +73,9 @@ __device__ __forceinline__ uint32_t pick_word(const uint4& r, uint32_t j) {
 #ifndef B2048_STREAM_THREADS
 #define B2048_STREAM_THREADS 1024
 #endif
+#ifndef B2048_V_W256
+#define B2048_V_W256 1     // 256-bit board loads / next-board stores (needs 32-byte aligned boards / next)
+#endif
 constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 
 // Shared-memory map of the streaming kernel (byte offsets from the start of dynamic smem).  All
@@ -138,10 +141,17 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
     // halves of the word times bytes {4,0} / {0,4}
     const uint32_t sl = cl ^ ((cl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
     const uint32_t sh = ch ^ ((ch >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+#ifdef B2048_DIAG_NOLDS
+    e0 = __dp2a_lo(sl, 0x04000004u, sbase) * 0x9E3779B1u;
+    e1 = __dp2a_hi(sl, 0x04000004u, sbase) * 0x9E3779B1u;
+    e2 = __dp2a_lo(sh, 0x04000004u, sbase) * 0x9E3779B1u;
+    e3 = __dp2a_hi(sh, 0x04000004u, sbase) * 0x9E3779B1u;
+#else
     e0 = lds32(__dp2a_lo(sl, 0x04000004u, sbase));
     e1 = lds32(__dp2a_hi(sl, 0x04000004u, sbase));
     e2 = lds32(__dp2a_lo(sh, 0x04000004u, sbase));
     e3 = lds32(__dp2a_hi(sh, 0x04000004u, sbase));
+#endif
   }
   uint32_t wl = __byte_perm(e0, e1, 0x5410);
   uint32_t wh = __byte_perm(e2, e3, 0x5410);
@@ -157,8 +167,12 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
   const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = SHR16(zh);
   const uint32_t ne_l = ne3_dirty(zl, v_l, add), ne_h = ne3_dirty(zh, v_h, add);
   const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = SHR16(n_h);
+#ifdef B2048_DIAG_NOPERP
+  const uint32_t up = 0, dn_l = 0, dn_h = 0; (void)n_l; (void)n_h; (void)ne_l; (void)ne_h; (void)nv_l; (void)nv_h;
+#else
   const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
+#endif
   // table index built on top of the row address with five predicated adds (no SEL, no final add)
   uint32_t fa = sa;
   if (changed) fa += 1u;
@@ -166,16 +180,28 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
   if (up) fa += 4u;
   if (dn_l | (dn_h & 0x0000FFFFu)) fa += 8u;
   if (fl & 0x80008000u) fa += 16u;
+#ifdef B2048_DIAG_NOFLAGS
+  flags = changed ? 1u : 0u; (void)fa;
+#else
   flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED | OVERFLOW
+#endif
 
   {
     const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
     wl ^= tl ^ (tl * xb.x);
     wh ^= th ^ (th * xb.x);
   }
+#ifdef B2048_DIAG_NOINV
+  olo = wl; ohi = wh;
+#else
   olo = prmt_raw(wl, wh, xa.z);
   ohi = prmt_raw(wl, wh, xa.w);
+#endif
+#ifdef B2048_DIAG_NOSPAWN
+  olo ^= changed ? w : 0u;
+#else
   finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags, add);
+#endif
 }
 
 // Cold path of the streaming kernel: recompute the four boards of one quad with the full table in
@@ -208,7 +234,7 @@ __device__ __noinline__ void fix_quad(uint32_t quad, const uint4* __restrict__ b
 }
 
 // ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
-// Requires 16-byte aligned boards/next/reward, 4-byte aligned actions/flags/override and n % 4 == 0
+// Requires 32-byte aligned boards/next, 16-byte aligned reward, 4-byte aligned actions/flags/override and n % 4 == 0
 // (the host wrapper sends the remainder and unaligned batches to step_small_kernel).
 template <bool HAS_OVERRIDE>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
@@ -264,8 +290,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   uint4 ba = make_uint4(0, 0, 0, 0), bb = ba;
   uint32_t a4 = 0, o4 = 0xFFFFFFFFu;
   if (quad < nq) {
+#if B2048_V_W256
+    ld_stream_v8(boards2 + 2u * quad, ba, bb);
+#else
     ba = ld_stream_v4(boards2 + 2u * quad);
     bb = ld_stream_v4(boards2 + 2u * quad + 1);
+#endif
     a4 = ld_stream_u32(actions4 + quad);
     if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
   }
@@ -278,15 +308,23 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     uint4 na = make_uint4(0, 0, 0, 0), nb = na;
     uint32_t an = 0, on = 0xFFFFFFFFu;
     if (nxt < nq) {
+#if B2048_V_W256
+      ld_stream_v8(boards2 + 2u * nxt, na, nb);
+#else
       na = ld_stream_v4(boards2 + 2u * nxt);
       nb = ld_stream_v4(boards2 + 2u * nxt + 1);
+#endif
       an = ld_stream_u32(actions4 + nxt);
       if (HAS_OVERRIDE) on = ld_stream_u32(override4 + nxt);
     }
 
     // one Philox4x32-10 call per aligned group of four global board indices
     const uint64_t pidx = pidx_base + quad;
+#ifdef B2048_DIAG_NOPHILOX
+    uint4 w = make_uint4((uint32_t)pidx * 0x9E3779B9u, (uint32_t)pidx * 0x85EBCA6Bu, s_lo * 0xC2B2AE35u ^ (uint32_t)pidx, (uint32_t)pidx * 0x27D4EB2Fu);
+#else
     uint4 w = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
+#endif
     if (base_mis != 0) {  // uniform: index_base not a multiple of 4 -> the quad straddles two calls
       const uint64_t p1 = pidx + 1;
       const uint4 w1 = philox4x32_10(make_uint4((uint32_t)p1, (uint32_t)(p1 >> 32), s_lo, s_hi), keys);
@@ -306,12 +344,21 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                                o4 & 0xFFu, n0l, n0h, rw0, f0, one);
     stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), mx, ba.z, ba.w, w.y, p4,
                                (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, one);
+#if B2048_V_W256
+    uint32_t n2l, n2h, n3l, n3h;
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), mx, bb.x, bb.y, w.z, p4,
+                               (o4 >> 16) & 0xFFu, n2l, n2h, rw2, f2, one);
+    stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), mx, bb.z, bb.w, w.w, p4,
+                               o4 >> 24, n3l, n3h, rw3, f3, one);
+    st_stream_v8(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h), make_uint4(n2l, n2h, n3l, n3h));
+#else
     st_stream_v4(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h));
     stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), mx, bb.x, bb.y, w.z, p4,
                                (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, one);
     stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), mx, bb.z, bb.w, w.w, p4,
                                o4 >> 24, n1l, n1h, rw3, f3, one);
     st_stream_v4(next2 + 2u * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
+#endif
     st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
     flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
     if (__builtin_expect(mx != LUT_LIM2, 0))   // some row of the quad was clamped: redo it from global memory
@@ -573,8 +620,9 @@ cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint
                         uint64_t* next, int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed,
                         uint64_t step, uint64_t index_base, uint32_t p4, const uint8_t* ovr,
                         cudaStream_t st) {
-  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next) |
-                         reinterpret_cast<uintptr_t>(reward)) & 15u) == 0 &&
+  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next)) &
+                        (B2048_V_W256 ? 31u : 15u)) == 0 &&
+                       (reinterpret_cast<uintptr_t>(reward) & 15u) == 0 &&
                        ((reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(flags) |
                          reinterpret_cast<uintptr_t>(ovr)) & 3u) == 0;
   int64_t done = 0;

@@ -16,6 +16,7 @@ int step_device(DeviceCtx* ctx, const uint64_t* boards, const uint8_t* actions, 
 
 static DeviceCtx g_ctx[MAX_DEVICES];
 static std::mutex g_mu;
+static std::mutex g_host_mu[MAX_DEVICES];   // b2048_step_host owns the device's staging slots for the whole call
 static std::vector<uint32_t> g_host_lut;
 
 // Canonical 2048 row move toward index 0 on four 4-bit exponents: compress, merge each tile at
@@ -132,9 +133,6 @@ extern "C" int b2048_init(int device) {
   if ((e = cudaMemcpy(c->lut, both.data(), both.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) !=
       cudaSuccess)
     return (int)e;
-  if ((e = cudaMalloc(&c->partials, MAX_PARTIALS * sizeof(double))) != cudaSuccess) return (int)e;
-  if ((e = cudaMalloc(&c->ticket, sizeof(unsigned int))) != cudaSuccess) return (int)e;
-  if ((e = cudaMemset(c->ticket, 0, sizeof(unsigned int))) != cudaSuccess) return (int)e;
   if ((e = env_kernels_configure()) != cudaSuccess) return (int)e;
   if ((e = qnet_kernels_configure()) != cudaSuccess) return (int)e;
   if ((e = wgrad_kernels_configure()) != cudaSuccess) return (int)e;
@@ -154,8 +152,6 @@ extern "C" int b2048_shutdown(int device) {
   cudaSetDevice(device);
   cudaDeviceSynchronize();
   cudaFree(c->lut);
-  cudaFree(c->partials);
-  cudaFree(c->ticket);
   if (c->ws) cudaFree(c->ws);
   for (int i = 0; i < 3; ++i) {
     if (c->ws_streams[i]) cudaStreamDestroy(c->ws_streams[i]);
@@ -195,6 +191,7 @@ extern "C" int b2048_step_host(const uint64_t* h_boards, const uint8_t* h_action
   int prev = 0;
   cudaGetDevice(&prev);
   if ((e = cudaSetDevice(device)) != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> host_lock(g_host_mu[device]);   // concurrent host calls on one device take turns
   {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!c->ws) {

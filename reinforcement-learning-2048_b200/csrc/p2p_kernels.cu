@@ -14,7 +14,17 @@ namespace b2048 {
 namespace {
 
 constexpr int P2P_THREADS = 256;
-constexpr long long SPIN_LIMIT = 1ll << 24;   // bounded wait: ~1 s of polling, then flag an error
+// Bounded wait: a peer that has not arrived after this long (wall clock, %globaltimer) is treated as lost.
+// The kernel then raises the error flag (sync_state[2], sticky) and leaves WITHOUT touching the replica:
+// summing a stale or half-written peer buffer would make the replicas diverge silently.  The host side
+// (PeerGradExchange.check, called wherever the trainers read a scalar back) turns the flag into an
+// exception.
+constexpr unsigned long long WAIT_LIMIT_NS = 30ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -30,12 +40,14 @@ __device__ __forceinline__ double ld_peer(const double* p) {   // peer data is w
   return v;
 }
 
-// wait until flags[i] >= epoch for all i < world (threads 0..world-1 poll one flag each)
-__device__ __forceinline__ void wait_flags(const uint64_t* flags, int world, uint64_t epoch, uint64_t* err) {
+// wait until flags[i] >= epoch for all i < world (threads 0..world-1 poll one flag each);
+// returns false (for every thread of the block) if the wait expired or the error flag is already up
+__device__ __forceinline__ bool wait_flags(const uint64_t* flags, int world, uint64_t epoch, uint64_t* err) {
   if ((int)threadIdx.x < world) {
-    long long spins = 0;
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
     while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-      if (++spins > SPIN_LIMIT) {
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > WAIT_LIMIT_NS) {
         st_release_sys(err, 1ull);
         break;
       }
@@ -43,6 +55,7 @@ __device__ __forceinline__ void wait_flags(const uint64_t* flags, int world, uin
     }
   }
   __syncthreads();
+  return ld_acquire_sys(err) == 0;
 }
 
 __global__ void __launch_bounds__(P2P_THREADS)
@@ -65,7 +78,7 @@ __global__ void __launch_bounds__(P2P_THREADS)
     s_step_size = lr / (1.0 - pow(b1, t));
     s_inv_bc2_sqrt = 1.0 / sqrt(1.0 - pow(b2, t));
   }
-  wait_flags(my_flags, world, epoch, sync_state + 2);
+  if (!wait_flags(my_flags, world, epoch, sync_state + 2)) return;   // a peer is missing: no update, error stays up
 
   // ---- sum over ranks in rank order + Adam ----------------------------------------------------------
   const double step_size = s_step_size, inv_bc2_sqrt = s_inv_bc2_sqrt;
@@ -89,7 +102,7 @@ __global__ void __launch_bounds__(P2P_THREADS)
   __syncthreads();
   if (!s_last) return;
   if ((int)threadIdx.x < world) st_release_sys(peer_flags[threadIdx.x] + world + rank, epoch);   // flag block 1
-  wait_flags(my_flags + world, world, epoch, sync_state + 2);
+  if (!wait_flags(my_flags + world, world, epoch, sync_state + 2)) return;   // epoch not published: the next call fails too
   if (threadIdx.x == 0) {
     sync_state[1] = 0;
     sync_state[0] = epoch;

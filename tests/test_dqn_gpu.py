@@ -110,6 +110,61 @@ def test_ddqn_target_loss_matches_reference(cuda, dq, tag):
     assert loss2.item() == loss.item()
 
 
+def test_ddqn_target_loss_is_reentrant_across_streams(cuda):
+    """include/b2048.h promises re-entrancy: the kernel owns no global scratch (one cluster, partial sums
+    through distributed shared memory), so many launches in flight on several streams all return the
+    bit-identical loss of a lone launch on the same data."""
+    B = 5000
+    g = torch.Generator(device="cpu").manual_seed(5)
+    sets = []
+    for k in range(3):
+        q = [torch.randn(B, 4, dtype=torch.float64, generator=g).to(cuda) for _ in range(3)]
+        a = torch.randint(0, 4, (B,), generator=g).to(cuda)
+        r = torch.randint(0, 64, (B,), generator=g).to(cuda)
+        dn = torch.randint(0, 2, (B,), generator=g).to(cuda)
+        sets.append((q, a, r, dn))
+    alone = []
+    for q, a, r, dn in sets:
+        loss, tgt, _, _ = ddqn.ddqn_target_loss(q[0], q[1], q[2], a, r, dn, 0.95, True)
+        torch.cuda.synchronize()
+        alone.append((loss.clone(), tgt.clone()))
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(3)]
+    got = [[] for _ in sets]
+    torch.cuda.synchronize()
+    for rep in range(40):                      # 120 launches queued back to back on three streams
+        for k, (q, a, r, dn) in enumerate(sets):
+            with torch.cuda.stream(streams[k]):
+                loss, tgt, _, _ = ddqn.ddqn_target_loss(q[0], q[1], q[2], a, r, dn, 0.95, True)
+                got[k].append((loss, tgt))
+    torch.cuda.synchronize()
+    for k in range(3):
+        for loss, tgt in got[k]:
+            assert torch.equal(loss, alone[k][0]) and torch.equal(tgt, alone[k][1])
+    # and against the numpy oracle
+    q, a, r, dn = sets[0]
+    t_ref, _, l_ref, _ = do.ddqn_target_loss(q[0].cpu().numpy(), q[1].cpu().numpy(), q[2].cpu().numpy(), a.cpu().numpy(),
+                                             r.cpu().numpy(), dn.cpu().numpy(), 0.95, True)
+    assert np.array_equal(alone[0][1].cpu().numpy(), t_ref)
+    np.testing.assert_allclose(float(alone[0][0].item()), l_ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("B", [1, 7, 511, 512, 4096, 4097, 70001])
+def test_ddqn_target_loss_sizes(cuda, B):
+    """Ragged batch sizes around the cluster's 8 x 512 threads, non-double branch included."""
+    g = torch.Generator(device="cpu").manual_seed(B)
+    q = [torch.randn(B, 4, dtype=torch.float64, generator=g).to(cuda) for _ in range(3)]
+    a = torch.randint(0, 4, (B,), generator=g).to(cuda)
+    r = torch.randint(0, 2048, (B,), generator=g).to(cuda)
+    dn = torch.randint(0, 2, (B,), generator=g).to(cuda)
+    for use_double in (True, False):
+        loss, tgt, qsa, grad = ddqn.ddqn_target_loss(q[0], q[1], q[2], a, r, dn, 0.8, use_double)
+        t_ref, q_ref, l_ref, g_ref = do.ddqn_target_loss(*[t.cpu().numpy() for t in q], a.cpu().numpy(), r.cpu().numpy(),
+                                                         dn.cpu().numpy(), 0.8, use_double)
+        assert np.array_equal(tgt.cpu().numpy(), t_ref) and np.array_equal(qsa.cpu().numpy(), q_ref)
+        assert np.array_equal(grad.cpu().numpy(), g_ref)
+        np.testing.assert_allclose(float(loss.item()), l_ref, rtol=1e-12)
+
+
 def test_ddqn_loss_autograd_matches_torch(cuda):
     """The autograd wrapper gives the online network the same gradient as the reference's
     expression written in torch (one_hot mask, sum, MSELoss(sum))."""
@@ -188,17 +243,17 @@ def _conv_net(d, prefix, cuda):
 def test_fused_conv_forward_matches_reference_q_values(cuda, golden_dir):
     """K6 against the Q tensors the reference's train_step computed with its own weights on its own
     sampled batch (tests/golden/dqn_conv.npz): states -> Q(s), next_states -> Q(s') for both networks.
-    Tolerance 1e-9 relative to the largest |Q| (float64, different summation order)."""
+    Tolerance (north_star): 1e-9 RELATIVE, element by element, with an absolute floor of 1e-12 for the
+    few Q-values that happen to be ~0 (float64, different summation order; measured ~1e-15)."""
     d = np.load(os.path.join(golden_dir, "dqn_conv.npz"))
     online, target = _conv_net(d, "w_", cuda), _conv_net(d, "tw_", cuda)
     fo, ft = b2048.qfused.FusedConvQ(online), b2048.qfused.FusedConvQ(target)
     s, s2 = torch.from_numpy(d["states"]).to(cuda), torch.from_numpy(d["next_states"]).to(cuda)
     for got, want in ((fo(s), d["q_cur"]), (fo(s2), d["q_next_online"]), (ft(s2), d["q_next_target"])):
-        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-9 * np.abs(want).max())
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-9, atol=1e-12)
     # packed boards in, exponent scaling == the float64 states the reference builds with log_scale()
     packed = dev_boards((2 ** d["next_states"].astype(np.int64)) * (d["next_states"] > 0), cuda)
-    np.testing.assert_allclose(fo.forward_boards(packed).cpu().numpy(), d["q_next_online"], rtol=0,
-                               atol=1e-9 * np.abs(d["q_next_online"]).max())
+    np.testing.assert_allclose(fo.forward_boards(packed).cpu().numpy(), d["q_next_online"], rtol=1e-9, atol=1e-12)
 
 
 @pytest.mark.parametrize("n", [1, 3, 31, 32, 33, 257, 2368, 4736, 5000, 5919, 70001])
@@ -217,12 +272,12 @@ def test_fused_conv_forward_sizes_and_scalings(cuda, n):
         for scaling, x in (("log2", x_log), ("normalized", x_norm)):
             want = net(x)
             got = fq.forward_boards(boards, scaling=scaling)
-            tol = 1e-9 * float(want.abs().max())
-            assert float((got - want).abs().max()) <= tol, (scaling, float((got - want).abs().max()), tol)
-            assert float((fq(x.contiguous()) - want).abs().max()) <= tol
+            tol = 1e-9 * want.abs() + 1e-12                   # element-wise relative + absolute floor
+            assert bool(((got - want).abs() <= tol).all()), (scaling, float((got - want).abs().max()))
+            assert bool(((fq(x.contiguous()) - want).abs() <= tol).all())
     if n <= 5000:                                         # and against the numpy oracle (pinned to the reference's Q tensors)
         want = do.conv_q_forward(x_log.reshape(n, 16).cpu().numpy(), *[p.detach().cpu().numpy() for p in net.parameters()])
-        assert np.abs(fq.forward_boards(boards).cpu().numpy() - want).max() <= 1e-9 * np.abs(want).max()
+        np.testing.assert_allclose(fq.forward_boards(boards).cpu().numpy(), want, rtol=1e-9, atol=1e-12)
     # the kernel reads the module's parameters at call time: an in-place weight change is seen
     with torch.no_grad():
         net[7].bias.add_(1.0)

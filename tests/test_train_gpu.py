@@ -110,16 +110,15 @@ def test_updater_graph_equals_eager_and_learns(cuda):
     a = DDQNUpdater(copy.deepcopy(base), ring, batch_size=5000, lr=1e-3, use_graph=False, seed=9)
     ring.head_size[2] = 0
     losses_a = [a.update().item() for _ in range(8)]
+    # graph mode: the warm-up + capture inside the first update() must leave no trace -- same
+    # losses, one optimizer step and one sample-counter bump per update(), from the very first call
     b = DDQNUpdater(copy.deepcopy(base), ring, batch_size=5000, lr=1e-3, use_graph=True, seed=9)
-    # graph capture runs 3 warm-up + 1 capture update: restore weights, optimizer state and counter
-    b.update()
-    b.model.load_state_dict(base.state_dict())
-    b.opt.exp_avg.zero_(); b.opt.exp_avg_sq.zero_(); b.opt.step_count.zero_()
-    b.graph = None
-    b.use_graph = False
     ring.head_size[2] = 0
     losses_b = [b.update().item() for _ in range(8)]
-    np.testing.assert_allclose(losses_a, losses_b, rtol=1e-9)
+    np.testing.assert_allclose(losses_a, losses_b, rtol=1e-12)
+    assert int(b.opt.step_count.item()) == 8 and int(ring.head_size[2].item()) == 8 and b.updates == 8
+    for p, q in zip(a.model.parameters(), b.model.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=1e-12, atol=1e-14)
     # the graph path itself: runs, advances the sample counter, changes weights, reduces the loss
     c = DDQNUpdater(copy.deepcopy(base), ring, batch_size=5000, lr=1e-3, use_graph=True, seed=9)
     first = c.update().item()
@@ -326,15 +325,17 @@ def test_batched_player_model_policy(cuda):
         pl._observe("sqrt", True)
 
 
-def test_checkpoint_resume_is_bit_identical(cuda, tmp_path):
-    """Save mid-run, keep going, reload, redo: same boards, same replay contents, same weights."""
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_checkpoint_resume_is_bit_identical(cuda, tmp_path, use_graph):
+    """Save mid-run, keep going, reload, redo: same boards, same replay contents, same weights -- also
+    in CUDA-graph mode, where load() drops the graph and the re-capture must not apply extra updates."""
     from b2048 import checkpoint
     torch.manual_seed(4)
 
     def make():
         ve = VectorEnv(2048, device=cuda, seed=21)
         ring = b2048.ReplayRing(15000, device=cuda)
-        up = DDQNUpdater(dense_model().to(cuda), ring, batch_size=512, lr=1e-3, conv=False, use_graph=False, seed=3)
+        up = DDQNUpdater(dense_model().to(cuda), ring, batch_size=512, lr=1e-3, conv=False, use_graph=use_graph, seed=3)
         return ve, ring, up
 
     def run(ve, ring, up, steps):
@@ -356,6 +357,7 @@ def test_checkpoint_resume_is_bit_identical(cuda, tmp_path):
     assert torch.equal(ve2.boards, want[0]) and torch.equal(ring2.s, want[1]) and torch.equal(ring2.head_size, want[2])
     for p, q in zip(up2.model.parameters(), want[3]):
         np.testing.assert_allclose(p.detach().cpu().numpy(), q.cpu().numpy(), rtol=1e-12, atol=1e-14)
+    assert int(up2.opt.step_count.item()) == 11 == up2.updates
 
 
 def test_batched_training_loop_follows_the_reference_schedule(cuda):
