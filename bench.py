@@ -46,6 +46,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+HBM_SPEC_GBS = 8000.0              # north_star's denominator ("~8 TB/s"); reported beside the measured copy peak
+
+
+def f64_peak_tflops():
+    """FP64 tensor-core peak measured on this pool's B200 with profiles/ubench/dmma_peak.cu
+    (mma.sync.m8n8k4.f64 = DMMA.8x8x4, the instruction K6 / K7 use; output committed beside the source)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ubench", "dmma_peak_b200.json")) as f:
+            return float(json.load(f)["f64_dmma_peak_tflops"]), "measured: profiles/ubench/dmma_peak.cu -> dmma_peak_b200.txt"
+    except Exception:
+        return 37.2, "derived: 148 SMs x 128 flop/clk x 1.965 GHz"
+
+
 def ncu_traffic_per_launch():
     """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
     try:
@@ -171,6 +184,32 @@ def cpu_baseline_sample():
                       f"({dt:.1f} s wall, {threads} pthreads, oracle/board_oracle.c)"}
 
 
+def reference_cpu_figures():
+    """The reference's OWN code (oracle/_ref, unmodified) timed on this host: C1 Player.play_game(random) and
+    C2 dqn_lib.train_step at batch 5000 (conv + dense); plus C1 again with this repo's drop-in
+    `board` module on the GPU (BASELINE config 1 through the per-call shim).  Each runs in its own process."""
+    import subprocess
+    script = os.path.join(ROOT, "oracle", "ref_bench.py")
+    cwd = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(os.path.join(cwd, ".git"), exist_ok=True)        # the reference's Experiment wants a git root (unused here)
+    out = {}
+
+    def run(tag, extra_args, timeout):
+        try:
+            r = subprocess.run([sys.executable, script] + extra_args, cwd=cwd, capture_output=True, text=True,
+                               timeout=timeout, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out[tag] = json.loads(line[-1]) if line else {"unavailable": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:          # noqa: BLE001 - a baseline that cannot run is reported, not fatal
+            out[tag] = {"unavailable": repr(e)[:300]}
+
+    run("reference_on_host_cpu", ["--device", "cpu", "--c1-seconds", "5", "--c2-calls", "2"], 240)
+    run("b2048_shim_player_loop", ["--engine", "b2048", "--device", "cuda", "--c1-seconds", "5", "--skip-c2"], 240)
+    out["kind"] = "reference"
+    out["cores"] = os.cpu_count()
+    return out
+
+
 def conv_qnet():
     from torch import nn   # reference configs/double_dqn_conv.py:19-28 (33 476 parameters, float64)
     return nn.Sequential(nn.Conv2d(1, 64, kernel_size=2), nn.ReLU(), nn.Conv2d(64, 64, kernel_size=2), nn.ReLU(),
@@ -222,7 +261,7 @@ def secondary_metrics(args, dev, rank, world, barrier):
 
     # rollout: random policy incl. legal mask, replay append and masked reset (5 launches + torch bookkeeping / step)
     nv = 1 << 22
-    ve = VectorEnv(nv, device=dev, seed=3, index_base=rank * nv)
+    ve = VectorEnv(nv, device=dev, seed=3, index_base=rank * nv, p_four=0.1)
     ring = b2048.ReplayRing(15000, device=dev)
     for _ in range(3):
         ve.step(replay=ring)
@@ -245,7 +284,7 @@ def secondary_metrics(args, dev, rank, world, barrier):
         "workload": "conv Q-net float64 forward of 1Mi packed boards per GPU, one kernel (DMMA), 168 960 flop/board",
         "boards_per_sec": world * nq / (ms * 1e-3), "ms_per_launch": ms, "fp64_TFLOPs_per_gpu": nq * 168960 / (ms * 1e-3) / 1e12}
     ng = 1 << 20
-    vg = VectorEnv(ng, device=dev, seed=5, index_base=rank * ng)
+    vg = VectorEnv(ng, device=dev, seed=5, index_base=rank * ng, p_four=0.1)
     for _ in range(3):
         vg.step(model=fq, epsilon=0.1, replay=ring)
     ms = timed(lambda i: vg.step(model=fq, epsilon=0.1, replay=ring), 10)
@@ -254,16 +293,87 @@ def secondary_metrics(args, dev, rank, world, barrier):
                                    "env_steps_per_sec": world * ng / (ms * 1e-3), "ms_per_step": ms}
     del vg, bq, qo
 
-    for name, net, conv in (("conv", conv_qnet, True), ("dense", dense_qnet, False)):
+    # K1 on the second distribution of SURVEY 8(d): boards after 64 random legal moves from reset (seed 2049).
+    # The shared-memory bank-conflict rate depends on the distribution; ncu counters for both are in profiles/.
+    ns = BOARDS_PER_GPU
+    bs = env.steady_state_boards(ns, seed=2049, index_base=rank * ns, device=dev)
+    as_ = env.random_actions(ns, seed=SEED_ACTIONS, index_base=rank * ns, device=dev)
+    os_ = (torch.empty_like(bs), torch.empty(ns, dtype=torch.int32, device=dev), torch.empty(ns, dtype=torch.uint8, device=dev))
+    for w in range(3):
+        env.step(bs, as_, seed=SEED_SPAWN, step_index=w, index_base=rank * ns, out=os_)
+    ms = timed(lambda i: env.step(bs, as_, seed=SEED_SPAWN, step_index=3 + i, index_base=rank * ns, out=os_), 20)
+    out["env_step_steady_state"] = {
+        "workload": "64Mi boards/GPU after 64 random legal moves from reset (SURVEY 8d 'rollout-steady-state', seed 2049) x 1 action",
+        "env_steps_per_sec": world * ns / (ms * 1e-3), "ms_per_launch": ms,
+        "algorithmic_GBps": ns * BYTES_PER_STEP / (ms * 1e-3) / 1e9}
+    del bs, as_, os_
+
+    # ---- DDQN updates/sec at batch 5000 (BASELINE.json's second metric): see the top-level "ddqn" block ----------
+    peak_tf, peak_src = f64_peak_tflops()
+    ddqn_block = {"metric": "ddqn_updates_per_sec", "batch_per_gpu": 5000, "global_batch": 5000 * world, "dtype": "f64",
+                  "f64_peak_tflops": peak_tf, "f64_peak_source": peak_src,
+                  "update": "sample(K2) + 3 forwards + fused target/loss(K3) + backward + gradient exchange + Adam, one CUDA graph"}
+    checks = {}
+    for name, net, conv, gflop in (("conv", conv_qnet, True, 4.2240), ("dense", dense_qnet, False, 20.1216)):
         torch.manual_seed(0)
         up = DDQNUpdater(net().to(dev), ring, batch_size=5000, gamma=0.8, lr=1e-2, conv=conv, use_graph=True)
         for _ in range(3):
             up.update()
         ms = timed(lambda i: up.update(), 100)
+        up.check()
+        tf = gflop / ms                                           # GFLOP / ms = TFLOP/s (per GPU)
+        ddqn_block[name] = {"updates_per_sec": 1e3 / ms, "ms_per_update": ms, "algorithmic_gflop_per_update": gflop,
+                            "fp64_tflops_per_gpu": tf, "frac_of_f64_peak": tf / peak_tf}
         out[f"ddqn_updates_{name}"] = {
             "workload": f"{name} Q-net float64, batch 5000/GPU, replay 15000, gamma 0.8 (f32), Double DQN, Adam; "
                         "sample+3 fwd+fused loss+bwd+allreduce+Adam in one CUDA graph",
             "updates_per_sec": 1e3 / ms, "ms_per_update": ms, "global_batch": 5000 * world}
+        if world > 1:                # replicas must be bit-identical after the fused NVLink allreduce + Adam (K5)
+            flat = up.params.flat.detach()
+            bits = flat.view(torch.int64)
+            mine = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev)).sum(),
+                                flat.sum().view(torch.int64)])
+            everyone = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(everyone, mine)
+            same = all(torch.equal(everyone[0], e) for e in everyone)
+            checks[name] = {"replicas_bit_identical": bool(same), "params_sum": float(flat.sum().item()),
+                            "hash": [int(v) for v in mine.tolist()][:2]}
+            if not same:
+                raise RuntimeError(f"{name}: parameter replicas differ across ranks after the gradient exchange")
+    if checks:
+        ddqn_block["replica_check"] = checks
+    out["__ddqn__"] = ddqn_block
+
+    # ---- BASELINE config 5 as stated: 8 Mi concurrent games per GPU (64 Mi on 8), per-GPU replay shard, conv Double DQN
+    # with the gradient exchange -- one combined step = one env step of every game (epsilon-greedy on the conv Q-net,
+    # replay append, auto-reset) + one update at batch 5000/GPU
+    n5 = 1 << 23
+    torch.manual_seed(0)
+    net5 = conv_qnet().to(dev)
+    ring5 = b2048.ReplayRing(15000, device=dev)
+    up5 = DDQNUpdater(net5, ring5, batch_size=5000, gamma=0.95, lr=1e-4, conv=True, use_graph=True)
+    v5 = VectorEnv(n5, device=dev, seed=17, index_base=rank * n5, p_four=0.1)
+    for _ in range(2):
+        v5.step(model=up5.i_model, epsilon=0.1, replay=ring5)
+        up5.update()
+    ms_env = timed(lambda i: v5.step(model=up5.i_model, epsilon=0.1, replay=ring5), 5)
+    ms_rand = timed(lambda i: v5.step(replay=ring5), 10)
+    ms_upd = timed(lambda i: up5.update(), 50)
+
+    def combined(i):
+        v5.step(model=up5.i_model, epsilon=0.1, replay=ring5)
+        up5.update()
+    ms_both = timed(combined, 5)
+    up5.check()
+    out["config5"] = {
+        "workload": f"{n5} concurrent games per GPU ({world * n5} total), epsilon-greedy (0.1) on the conv Q-net (K6) + K1 + replay "
+                    "shard (K2 append) + auto-reset, and one conv Double-DQN update per step at batch 5000/GPU, gamma 0.95, "
+                    "gradient exchange over NVLink (K5) at N > 1",
+        "combined_step_ms": ms_both, "env_steps_per_sec": world * n5 / (ms_both * 1e-3), "updates_per_sec": 1e3 / ms_both,
+        "env_step_alone_ms": ms_env, "env_steps_per_sec_alone": world * n5 / (ms_env * 1e-3),
+        "random_policy_step_alone_ms": ms_rand, "random_policy_env_steps_per_sec": world * n5 / (ms_rand * 1e-3),
+        "update_alone_ms": ms_upd, "updates_per_sec_alone": 1e3 / ms_upd, "global_batch": 5000 * world}
+    del v5, up5, ring5
     # the whole loop: batched Double-DQN training with the reference's conv config and schedule
     # (train_batched: epsilon-greedy rollouts on K6 -> replay ring -> one update per finished episode)
     import time
@@ -348,10 +458,15 @@ def run_ours(args):
         return
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----------------------
-    hb, ha = boards.cpu().pin_memory(), actions.cpu().pin_memory()
-    hn = torch.empty(n, dtype=torch.int64).pin_memory()
-    hr = torch.empty(n, dtype=torch.int32).pin_memory()
-    hf = torch.empty(n, dtype=torch.uint8).pin_memory()
+    # Pinned buffers come from b2048_host_alloc: placed on the NUMA node next to this rank's GPU, and the calling
+    # thread is bound there too, so that N ranks do not stage through the far socket.
+    env.bind_thread_near(local)
+    pb = {k: env.PinnedBuffer(n, dt, device=local) for k, dt in
+          (("boards", "int64"), ("actions", "uint8"), ("next", "int64"), ("reward", "int32"), ("flags", "uint8"))}
+    hb, ha, hn, hr, hf = (pb[k].tensor for k in ("boards", "actions", "next", "reward", "flags"))
+    hb.copy_(boards)
+    ha.copy_(actions)
+    torch.cuda.synchronize()
     e2e_steps = max(1, min(args.steps, 5))
     env.step_host(hb, ha, hn, hr, hf, seed=SEED_SPAWN, step_index=0, index_base=base, device=local)
     barrier()
@@ -360,9 +475,38 @@ def run_ours(args):
         env.step_host(hb, ha, hn, hr, hf, seed=SEED_SPAWN, step_index=1 + k, index_base=base, device=local)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # what the link itself gives, all ranks at once: plain copies of the same buffers, one direction at a time
+    # and both together (the ceiling of the e2e figure: 9 B/step up, 13 B/step down)
+    link = {}
+    scratch = torch.empty(n, dtype=torch.int64, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    for tag in ("h2d", "d2h", "both"):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            if tag in ("h2d", "both"):
+                boards.copy_(hb, non_blocking=True)
+            if tag in ("d2h", "both"):
+                with torch.cuda.stream(side):
+                    hn.copy_(scratch, non_blocking=True)
+        barrier()
+        link[tag] = time.perf_counter() - t0
+    del scratch
+    link_t = torch.tensor([link["h2d"], link["d2h"], link["both"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(link_t, op=dist.ReduceOp.MAX)
+    gb = 3 * n * 8 / 1e9
+    e2e_link = {"h2d_GBps_per_gpu": gb / float(link_t[0]), "d2h_GBps_per_gpu": gb / float(link_t[1]),
+                "bidirectional_GBps_per_gpu_each_way": gb / float(link_t[2]), "concurrent_ranks": world,
+                "pinned_numa_node": pb["boards"].numa_node, "numa_bound": pb["boards"].bound,
+                "what": "cudaMemcpyAsync of 512 MiB pinned <-> device on every rank at once (max time over ranks)"}
+    e2e_link["e2e_ceiling_steps_per_sec"] = world * min(e2e_link["bidirectional_GBps_per_gpu_each_way"] * 1e9 / 13.0,
+                                                        e2e_link["h2d_GBps_per_gpu"] * 1e9 / 9.0)
     sampler.stop_flag = True
 
     extra = secondary_metrics(args, dev, rank, world, barrier)
+    ddqn_block = extra.pop("__ddqn__")
+    extra["e2e_link"] = e2e_link
 
     times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -385,16 +529,30 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "steps/s",
                     "h2d_bytes_per_step": n * 9, "d2h_bytes_per_step": n * 13, "steps": e2e_steps,
-                    "api": "b2048_step_host (pinned host buffers, 3-slot H2D|kernel|D2H pipeline)"},
+                    "api": "b2048_step_host (NUMA-local pinned host buffers from b2048_host_alloc, 3-slot H2D|kernel|D2H pipeline)",
+                    "link_ceiling_steps_per_sec": e2e_link["e2e_ceiling_steps_per_sec"]},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
                          "kernel": "step_stream_kernel<false>", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "peak_source": peak_src},
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "peak_source": peak_src,
+                         "peak_spec": HBM_SPEC_GBS, "frac_vs_spec": achieved / HBM_SPEC_GBS,
+                         "steady_state_distribution": {"achieved": extra["env_step_steady_state"]["algorithmic_GBps"],
+                                                       "frac": extra["env_step_steady_state"]["algorithmic_GBps"] / peak}},
+            "ddqn": ddqn_block,
         }
         line["extra"] = extra
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample()
+            ref = reference_cpu_figures()
+            extra["reference_cpu"] = ref
+            host = ref.get("reference_on_host_cpu", {})
+            for name in ("conv", "dense"):
+                c2 = host.get(f"c2_train_step_{name}", {})
+                if "updates_per_sec" in c2:
+                    ddqn_block[name]["reference_cpu_updates_per_sec"] = c2["updates_per_sec"]
+                    ddqn_block[name]["reference_cpu"] = (f"dqn_lib.train_step of the unmodified reference on this host, "
+                                                         f"{host.get('torch_threads')} torch threads of {host.get('cpu_count')} CPUs")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

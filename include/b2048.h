@@ -30,13 +30,16 @@
 #ifndef B2048_H_
 #define B2048_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define B2048_ABI_VERSION 1
+/* 2: spawn stream v2 (one 16-bit Philox lane per board, eight boards per call; see b2048_step);
+ *    boards / next of b2048_step and next4 of b2048_step_all4 take the fast path when 32-byte aligned. */
+#define B2048_ABI_VERSION 2
 
 /* ---- error codes (negative; positive values are cudaError_t) ------------------------------ */
 #define B2048_OK 0
@@ -61,8 +64,8 @@ extern "C" {
 #define B2048_SPAWN_NONE 0xFFu
 #define B2048_SPAWN_SKIP 0xFEu
 
-/* p4_threshold: a spawned tile is a "4" iff (w << 16) < p4_threshold (32-bit unsigned), i.e. the
- * low 16 bits of the board's Philox word w are a uniform fraction compared with p4_threshold/2^32.
+/* p4_threshold: a spawned tile is a "4" iff frac < p4_threshold (32-bit unsigned), where frac is the
+ * board's 16-bit uniform fraction in the upper half of a 32-bit word (see b2048_step: Spawn).
  * 0x1999999A = 10 % (north_star), 0x80000000 = 50 % (the reference, src/board.py:12,49). */
 #define B2048_P4_TEN_PERCENT   0x1999999Au
 #define B2048_P4_FIFTY_PERCENT 0x80000000u
@@ -90,9 +93,14 @@ int b2048_copy_row_lut_host(uint32_t* out65536);
  *   next[i]   = slide/merge of boards[i] by actions[i], plus one spawned tile iff changed
  *   reward[i] = sum of merged tile values of this move
  *   flags[i]  = B2048_FLAG_* (legal mask and done are properties of the INPUT board)
- * Spawn: board g = index_base + i owns one 32-bit word w = word (g & 3) of the Philox4x32-10 call
- * with key `seed` and counter (g >> 2, `step`); cell = k-th empty cell of the slid board
- * (row-major) with k = floor(w * n_empty / 2^32); value "4" iff (w << 16) < p4_threshold.
+ * Spawn (stream v2): board g = index_base + i owns one 16-bit lane d of the Philox4x32-7 call with key
+ * `seed` and counter (g >> 3, `step`): lane g & 7 = half (g & 1) of output word ((g & 7) >> 1), low
+ * half first.  With n = number of empty cells of the slid board: cell = k-th empty cell (row-major),
+ * k = floor(d * n / 65536); value "4" iff (((d * n) mod 65536) << 16) < p4_threshold.  (One 32x32->64
+ * product (d << 16) * n yields k in its high and the fraction in its low word.  For odd n the
+ * fraction is exactly uniform, for even n uniform over multiples of n's power of two; a cell's
+ * probability differs from 1/n by at most 2^-16.  Seven rounds: the smallest Crush-resistant Philox4x32
+ * (Salmon et al., SC'11; Random123's philox4x32_7); every other stream of this library uses ten.)
  * The result depends only on (seed, step, g, board, action), never on n or on the sharding.
  * spawn_override (nullable, n bytes) replays a given (cell, value) instead — the parity hook.
  * actions[i] > 3 is treated as actions[i] & 3. */
@@ -103,7 +111,8 @@ int b2048_step(const uint64_t* boards, const uint8_t* actions, uint64_t* next, i
 /* All four actions per board (BASELINE.json config 2; = Board2048.available_moves,
  * src/board.py:138-145).  next4[i*4+a], reward4[i*4+a]; flags[i] bits 0-3 = legal mask, bit 4 =
  * done, bit 6 = overflow in any direction.  Successor a equals b2048_step's output for action a
- * (same Philox words).  spawn_override4 (nullable) is n*4 bytes. */
+ * (same Philox lane).  next4 must be 32-byte aligned, reward4 16-byte aligned (B2048_EINVAL
+ * otherwise); spawn_override4 (nullable) is n*4 bytes, 4-byte aligned. */
 int b2048_step_all4(const uint64_t* boards, uint64_t* next4, int32_t* reward4, uint8_t* flags,
                     int64_t n, uint64_t seed, uint64_t step, uint64_t index_base,
                     uint32_t p4_threshold, const uint8_t* spawn_override4, void* stream);
@@ -152,6 +161,15 @@ int b2048_random_boards(uint64_t* boards, int64_t n, uint64_t seed, uint64_t ind
                         uint32_t p_empty_threshold, uint32_t max_exp, void* stream);
 int b2048_random_actions(uint8_t* actions, int64_t n, uint64_t seed, uint64_t step,
                          uint64_t index_base, void* stream);
+
+/* Pinned host memory for b2048_step_host, placed on the NUMA node next to `device`: the calling thread is
+ * bound to the GPU's local CPUs (sysfs local_cpulist) while the pages are allocated and first touched, then
+ * its affinity is restored.  *numa_node_out = that node (-1 unknown), *bound_out = 1 if the binding was
+ * applied (both nullable).  Falls back to a plain cudaHostAlloc when the topology cannot be read. */
+int b2048_host_alloc(void** out, size_t bytes, int device, int* numa_node_out, int* bound_out);
+int b2048_host_free(void* p);
+/* Bind the calling host thread to the CPUs next to `device` (the thread that calls b2048_step_host). */
+int b2048_bind_thread_near(int device);
 
 /* Same as b2048_step but with HOST buffers: chunks the batch and overlaps H2D copy, kernel and
  * D2H copy on internal streams; returns after everything has landed in the host buffers.

@@ -163,12 +163,13 @@ void oracle_unpack(uint64_t b, int64_t* tiles) {
   }
 }
 
-/* Philox4x32-10, restated from Salmon et al. SC'11 (Random123 philox.h constants), to let the
- * oracle predict the library's spawn stream.  Checked against the Random123 known-answer vectors
- * in tests/test_oracle_golden.py. */
-void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* Philox4x32-R, restated from Salmon et al. SC'11 (Random123 philox.h constants), to let the
+ * oracle predict the library's streams.  R = 10 is checked against the Random123 known-answer vectors
+ * in tests/test_oracle_golden.py; the spawn stream uses R = 7 (Random123's philox4x32_7), all other
+ * streams R = 10. */
+void oracle_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < rounds; ++i) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -182,24 +183,31 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  oracle_philox4x32_r(ctr, key, out, 10);
+}
 
+#define SPAWN_PHILOX_ROUNDS 7
 #define DOM_SPAWN 0x00000000u
 #define DOM_RESET 0x5BD1E995u
 
-/* The library's spawn stream (include/b2048.h): board g uses word (g & 3) of the Philox4x32-10
- * call with counter (g >> 2, step) and key (seed ^ domain). */
-static uint32_t spawn_word(uint64_t seed, uint64_t step, uint64_t g) {
-  const uint64_t pidx = g >> 2;
+/* The library's spawn stream, ABI version 2 (include/b2048.h): board g owns the 16-bit lane (g & 7) of
+ * the Philox4x32-7 call with counter (g >> 3, step) and key (seed ^ domain); lane j is half (j & 1)
+ * of output word (j >> 1), low half first.  Returns the lane value d, 0..65535. */
+uint32_t oracle_spawn_draw(uint64_t seed, uint64_t step, uint64_t g) {
+  const uint64_t pidx = g >> 3;
   const uint32_t ctr[4] = {(uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ DOM_SPAWN};
   uint32_t o[4];
-  oracle_philox4x32_10(ctr, key, o);
-  return o[g & 3];
+  oracle_philox4x32_r(ctr, key, o, SPAWN_PHILOX_ROUNDS);
+  const uint32_t lane = (uint32_t)(g & 7u), w = o[lane >> 1];
+  return (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
 }
 
 /* Batched step on packed boards with the library's documented spawn rule (include/b2048.h):
- * cell = k-th empty (row-major), k = floor(w * n_empty / 2^32); "4" iff (w << 16) < p4_threshold;
- * spawn_override[i] != 0xFF replays (cell | exp << 4). */
+ * with d = the board's 16-bit draw and n = number of empty cells of the slid board,
+ * cell = k-th empty (row-major), k = floor(d * n / 65536); "4" iff (((d * n) mod 65536) << 16) <
+ * p4_threshold; spawn_override[i] != 0xFF replays (cell | exp << 4). */
 static void step_packed_range(const uint64_t* boards, const uint8_t* actions, uint64_t* next,
                               int32_t* reward, uint8_t* flags, int64_t begin, int64_t end,
                               uint64_t seed, uint64_t step, uint64_t index_base,
@@ -210,17 +218,21 @@ static void step_packed_range(const uint64_t* boards, const uint8_t* actions, ui
     int cell = -1;
     int64_t val = 0;
     int f;
-    if (spawn_override && spawn_override[i] != 0xFF) {
+    if (spawn_override && spawn_override[i] == 0xFE) {          /* B2048_SPAWN_SKIP: slide-only result */
+      f = oracle_step_tiles(in, actions[i] & 3, -1, 0, out, &r);
+    } else if (spawn_override && spawn_override[i] != 0xFF) {
       cell = spawn_override[i] & 0xF;
       val = (int64_t)1 << (spawn_override[i] >> 4);
       f = oracle_step_tiles(in, actions[i] & 3, cell, val, out, &r);
     } else {
       f = oracle_step_tiles(in, actions[i] & 3, -1, 0, out, &r);
       if (f & F_CHANGED) {
-        const uint32_t w = spawn_word(seed, step, index_base + (uint64_t)i);
-        const int ne = count_empty(out);
-        const int rank = (int)(((uint64_t)w * (uint64_t)ne) >> 32);
-        oracle_populate(out, rank, ((uint32_t)(w << 16) < p4_threshold) ? 4 : 2);
+        const uint32_t d = oracle_spawn_draw(seed, step, index_base + (uint64_t)i);
+        const uint32_t ne = (uint32_t)count_empty(out);
+        const uint32_t prod = d * ne;                       /* < 2^20 */
+        const int rank = (int)(prod >> 16);
+        const uint32_t frac = (prod & 0xFFFFu) << 16;
+        oracle_populate(out, rank, (frac < p4_threshold) ? 4 : 2);
       }
     }
     /* 32768 + 32768 does not fit a nibble: the library flags it and leaves next/reward unspecified */
@@ -229,6 +241,44 @@ static void step_packed_range(const uint64_t* boards, const uint8_t* actions, ui
     next[i] = oracle_pack(out);
     reward[i] = (int32_t)r;
     flags[i] = (uint8_t)f;
+  }
+}
+
+/* The library's synthetic-input generators (b2048_random_boards / b2048_random_actions, include/b2048.h),
+ * restated so that the bench stream exists on a CPU-only box too: oracle/gen_golden.py feeds its first
+ * 65536 boards to the reference, and __graft_entry__.smoke() checks the kernel against those goldens.
+ * Board g: 8 Philox calls (counter (g, q), q = 0..7, domain BOARDS), words (x,y) and (z,w) give cells
+ * 2q and 2q+1: empty iff the first word < p_empty_threshold, else exponent 1 + floor(second * max_exp / 2^32).
+ * Action g: word (g & 3) of the call with counter (g >> 2, step), domain ACTIONS; action = word >> 30. */
+#define DOM_BOARDS 0x1B873593u
+#define DOM_ACTIONS 0xCC9E2D51u
+void oracle_stream_boards(uint64_t* boards, int64_t n, uint64_t seed, uint64_t index_base,
+                          uint32_t p_empty_threshold, uint32_t max_exp) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ DOM_BOARDS};
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t g = index_base + (uint64_t)i;
+    uint64_t b = 0;
+    for (uint32_t q = 0; q < 8; ++q) {
+      const uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), q, 0u};
+      uint32_t o[4];
+      oracle_philox4x32_10(ctr, key, o);
+      const uint64_t e0 = (o[0] < p_empty_threshold) ? 0u : 1u + (uint32_t)(((uint64_t)o[1] * max_exp) >> 32);
+      const uint64_t e1 = (o[2] < p_empty_threshold) ? 0u : 1u + (uint32_t)(((uint64_t)o[3] * max_exp) >> 32);
+      b |= e0 << (8 * q);
+      b |= e1 << (8 * q + 4);
+    }
+    boards[i] = b;
+  }
+}
+
+void oracle_stream_actions(uint8_t* actions, int64_t n, uint64_t seed, uint64_t step, uint64_t index_base) {
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ DOM_ACTIONS};
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t g = index_base + (uint64_t)i, pidx = g >> 2;
+    const uint32_t ctr[4] = {(uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+    uint32_t o[4];
+    oracle_philox4x32_10(ctr, key, o);
+    actions[i] = (uint8_t)(o[g & 3] >> 30);
   }
 }
 

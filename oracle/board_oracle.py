@@ -237,6 +237,29 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def stream_boards(n: int, seed: int = 2048, index_base: int = 0, p_empty: float = 0.3, max_exp: int = 11) -> np.ndarray:
+    """The library's own synthetic board stream (b2048_random_boards), bit for bit, on the CPU."""
+    L = lib()
+    L.oracle_stream_boards.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64,
+                                       ctypes.c_uint32, ctypes.c_uint32]
+    L.oracle_stream_boards.restype = None
+    out = np.zeros(n, dtype=np.uint64)
+    thr = max(0, min(0xFFFFFFFF, int(round(p_empty * 4294967296.0))))     # = b2048.env.p4_threshold
+    L.oracle_stream_boards(_p(out, ctypes.c_uint64), n, seed & (2**64 - 1), index_base & (2**64 - 1), thr, max_exp)
+    return out
+
+
+def stream_actions(n: int, seed: int = 2050, step: int = 0, index_base: int = 0) -> np.ndarray:
+    """The library's own synthetic action stream (b2048_random_actions), bit for bit, on the CPU."""
+    L = lib()
+    L.oracle_stream_actions.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64,
+                                        ctypes.c_uint64]
+    L.oracle_stream_actions.restype = None
+    out = np.zeros(n, dtype=np.uint8)
+    L.oracle_stream_actions(_p(out, ctypes.c_uint8), n, seed & (2**64 - 1), step & (2**64 - 1), index_base & (2**64 - 1))
+    return out
+
+
 def random_boards(n: int, seed: int, p_empty: float = 0.3, max_exp: int = 11) -> np.ndarray:
     """numpy-side synthetic boards with the distribution of SURVEY.md §8(d) (not bit-equal to the
     library's Philox generator; used where only the distribution matters)."""

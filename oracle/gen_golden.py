@@ -143,11 +143,11 @@ def gen_boards(n_per_kind=600):
 
 
 # --------------------------------------------------------------------------------------------
-def gen_games(n_games=30):
+def gen_games(n_games=30, save=True, seed=7):
     """Full reference episodes through dqn_lib.play_one_step with epsilon = 1 (random actions,
     illegal no-ops included, final dead->dead transition with done=1; src/dqn_lib.py:91-107)."""
-    random.seed(7)
-    np.random.seed(7)
+    random.seed(seed)
+    np.random.seed(seed)
     S, A, R, S2, D, G = [], [], [], [], [], []
     buf = deque(maxlen=10 ** 6)
     for g in range(n_games):
@@ -162,6 +162,8 @@ def gen_games(n_games=30):
             D.append(int(bool(done)))
             G.append(g)
             b = nb
+    if not save:
+        return buf
     np.savez_compressed(os.path.join(OUT, "games.npz"), state=np.array(S, dtype=np.int64),
                         action=np.array(A, dtype=np.uint8), reward=np.array(R, dtype=np.int64),
                         next=np.array(S2, dtype=np.int64), done=np.array(D, dtype=np.uint8),
@@ -246,6 +248,95 @@ def gen_dqn(buf: deque):
         print(f"dqn_{name}.npz", "loss", out["loss_double"], out["loss_single"])
 
 
+def gen_dqn_config3():
+    """BASELINE.json config 3 as stated: dense Q-net, batch 5000, gamma 0.95 (and the config module's own
+    0.80) through the reference's sample_experiences / train_step.  gamma is applied in float32 by the
+    reference: 0.95 and 0.80 round differently, so each needs its own recorded targets.
+    The 403 716 weights are not shipped (3.2 MB per network): the Q tensors the reference computed are."""
+    import configs.double_dqn_dense as cdense
+    import copy
+    buf = gen_games(n_games=40, save=False, seed=11)
+    trans = list(buf)[:6000]
+    rb = deque(trans, maxlen=len(trans))
+    B = 5000
+    torch.manual_seed(4321)
+    model = copy.deepcopy(cdense.model).cpu()
+    for p in model.parameters():
+        p.data = torch.randn_like(p) * 0.05
+    target = copy.deepcopy(model)
+    for p in target.parameters():
+        p.data = p.data + torch.randn_like(p) * 0.02
+    out = dict(
+        buf_state=np.array([t[0].state.reshape(16) for t in trans], dtype=np.int64),
+        buf_action=np.array([t[1] for t in trans], dtype=np.uint8),
+        buf_reward=np.array([int(t[2]) for t in trans], dtype=np.int64),
+        buf_next=np.array([t[3].state.reshape(16) for t in trans], dtype=np.int64),
+        buf_done=np.array([int(bool(t[4])) for t in trans], dtype=np.uint8),
+    )
+    np.random.seed(2051)
+    out["idx"] = np.random.randint(len(rb), size=B).astype(np.int64)
+    np.random.seed(2051)
+    st, ac, rw, ns, dn = ref_dqn.sample_experiences(B, rb, "cpu", ref_dqn.board_as_flattened_tensor,
+                                                    ref_dqn.extract_samples_dense)
+    out.update(states=st.numpy().reshape(B, 16), actions=ac.numpy(), rewards=rw.numpy(),
+               next_states=ns.numpy().reshape(B, 16), dones=dn.numpy())
+    with torch.no_grad():
+        out["q_next_online"] = model(ns).numpy()
+        out["q_next_target"] = target(ns).numpy()
+        out["q_cur"] = model(st).numpy()
+    for gamma, gtag in ((0.95, "g095"), (0.80, "g080")):
+        for use_double in (True, False):
+            rec = {}
+            base_loss = torch.nn.MSELoss(reduction="sum")
+
+            def recording_loss(q, t, rec=rec):
+                rec["q"] = q.detach().numpy().copy()
+                rec["t"] = t.detach().numpy().copy()
+                return base_loss(q, t)
+
+            opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+            np.random.seed(2051)
+            loss = ref_dqn.train_step(B, gamma, model, target, rb, recording_loss, opt, "cpu", use_double,
+                                      ref_dqn.board_as_flattened_tensor, ref_dqn.extract_samples_dense)
+            tag = f"{gtag}_{'double' if use_double else 'single'}"
+            out[f"target_{tag}"] = rec["t"]
+            out[f"q_sa_{tag}"] = rec["q"]
+            out[f"loss_{tag}"] = np.float64(loss.item())
+            for p in list(model.parameters()) + list(target.parameters()):
+                p.grad = None
+    np.savez_compressed(os.path.join(OUT, "dqn_dense_b5000.npz"), **out)
+    print("dqn_dense_b5000.npz", {k: float(v) for k, v in out.items() if k.startswith("loss_")})
+
+
+def gen_bench_stream(n=65536):
+    """SURVEY 8(d) 'parity subset for every run': the first 65536 boards and actions of the BENCH stream
+    (b2048_random_boards seed 2048 / b2048_random_actions seed 2050, restated in oracle/board_oracle.c) through
+    the reference's Board2048: slide-only successor, merge-score reward, legal mask.  __graft_entry__.smoke()
+    and tests/test_env_gpu.py compare the CUDA path with these, spawn switched off through the override hook."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import board_oracle as bo
+    boards = bo.stream_boards(n, seed=2048)
+    actions = bo.stream_actions(n, seed=2050, step=0)
+    tiles = bo.unpack(boards)
+    slide = np.zeros(n, dtype=np.uint64)
+    reward = np.zeros(n, dtype=np.int32)
+    legal = np.zeros(n, dtype=np.uint8)
+    sh = 4 * np.arange(16, dtype=np.uint64)
+    for i in range(n):
+        s = tiles[i]
+        m = mk(s).available_moves_as_torch_unit_vector(device="cpu")      # src/board.py:128-135
+        legal[i] = sum(1 << a for a in range(4) if float(m[a]) != 0)
+        sl, r, _ = move_with_and_without_spawn(s, int(actions[i]))
+        e = np.where(sl.reshape(16) > 0, np.log2(np.maximum(sl.reshape(16), 1)).astype(np.uint64), 0).astype(np.uint64)
+        slide[i] = (e << sh).sum(dtype=np.uint64)
+        reward[i] = r
+        if i % 8192 == 0:
+            print("bench stream", i, "/", n)
+    np.savez_compressed(os.path.join(OUT, "bench_stream.npz"), boards=boards, actions=actions, slide=slide,
+                        reward=reward, legal=legal)
+    print("bench_stream.npz", n, "legal histogram", np.bincount(legal, minlength=16).tolist())
+
+
 def gen_egreedy(n_model=300, n_synth=3000):
     """epsilon_greedy_policy (greedy branch, src/dqn_lib.py:23-30) on boards with real and
     synthetic Q-values (ties, all-negative and all-positive rows, illegal best moves)."""
@@ -301,3 +392,7 @@ if __name__ == "__main__":
         gen_dqn(buf)
     if "egreedy" in which:
         gen_egreedy()
+    if "config3" in which:
+        gen_dqn_config3()
+    if "bench_stream" in which:
+        gen_bench_stream()

@@ -96,6 +96,46 @@ k(const uint4* __restrict__ boards2, const uint32_t* __restrict__ actions4, uint
   }
 }
 
+template <int THREADS, int MAP, int SMODE>
+__global__ void __launch_bounds__(THREADS, 1)
+k8(const uint4* __restrict__ boards2, const uint32_t* __restrict__ actions4, uint4* __restrict__ next2,
+   uint4* __restrict__ reward4, uint32_t* __restrict__ flags4, uint32_t noct, int work, uint32_t salt) {
+  extern __shared__ unsigned char smem[];
+  if (salt == 0xFFFFFFFFu) smem[threadIdx.x] = 1;
+  const uint32_t stride = gridDim.x * THREADS;
+  uint32_t oct = blockIdx.x * THREADS + threadIdx.x;
+  auto qa_of = [](uint32_t o) { return MAP == 0 ? 2u * o : ((o >> 5) << 6) + (o & 31u); };
+  auto qb_of = [](uint32_t o) { return MAP == 0 ? 2u * o + 1u : ((o >> 5) << 6) + (o & 31u) + 32u; };
+  uint4 xa = make_uint4(0, 0, 0, 0), xb = xa, ya = xa, yb = xa;
+  uint32_t ax = 0, ay = 0;
+  if (oct < noct) { U8 v = ldv8(boards2 + 2u * qa_of(oct), 0); xa = v.a; xb = v.b; ax = ld32(actions4 + qa_of(oct)); }
+  while (oct < noct) {
+    { U8 v = ldv8(boards2 + 2u * qb_of(oct), 0); ya = v.a; yb = v.b; ay = ld32(actions4 + qb_of(oct)); }
+    for (int half = 0; half < 2; ++half) {
+      const uint4 ua = half ? ya : xa, ub = half ? yb : xb;
+      const uint32_t xact = half ? ay : ax, quad = half ? qb_of(oct) : qa_of(oct);
+      uint32_t c0 = ua.x ^ salt, c1 = ua.z, c2 = ub.x, c3 = ub.z;
+      for (int w = 0; w < work; ++w) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(c0) : "r"(c1), "r"(xact));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(c1) : "r"(salt), "r"(c2));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(c2) : "r"(c3), "r"(xact));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(c3) : "r"(salt), "r"(c0));
+        }
+      }
+      stv8(next2 + 2u * quad, make_uint4(c0, ua.y, c1, ua.w), make_uint4(c2, ub.y, c3, ub.w), SMODE);
+      stv4(reward4 + quad, make_uint4(c0, c1, c2, c3), SMODE);
+      flags4[quad] = xact ^ c0;
+      if (half == 0) {
+        const uint32_t nxt = oct + stride;
+        if (nxt < noct) { U8 v = ldv8(boards2 + 2u * qa_of(nxt), 0); xa = v.a; xb = v.b; ax = ld32(actions4 + qa_of(nxt)); }
+      }
+    }
+    oct += stride;
+  }
+}
+
 struct Bufs { uint4 *boards, *next, *reward; uint32_t *actions, *flags; };
 
 template <int THREADS, int PF, int LMODE, int SMODE, bool W256 = false>
@@ -117,6 +157,25 @@ void run(const char* name, const Bufs& b, uint32_t nq, int grid, int smem, int w
          (double)nq * 88.0 / best / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+template <int THREADS, int MAP, int SMODE>
+void run8(const char* name, const Bufs& b, uint32_t nq, int grid, int smem, int work) {
+  auto kern = k8<THREADS, MAP, SMODE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int i = 0; i < 3; ++i) kern<<<grid, THREADS, smem>>>(b.boards, b.actions, b.next, b.reward, b.flags, nq / 2, work, 17);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e9f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    for (int i = 0; i < 10; ++i) kern<<<grid, THREADS, smem>>>(b.boards, b.actions, b.next, b.reward, b.flags, nq / 2, work, 17 + i);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
+    if (ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  printf("%-44s grid %4d smem %6d work %3d : %.4f ms  %6.0f GB/s%s\n", name, grid, smem, work, best,
+         (double)nq * 88.0 / best / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main() {
   const uint32_t nq = (1u << 26) / 4;
   Bufs b;
@@ -126,6 +185,11 @@ int main() {
   const int BIG = 229664;   // the dynamic shared memory K1 asks for (forces one CTA per SM)
   printf("# 64 Mi boards, 22 B/board = 1476 MB per launch; work = dummy 32-instruction blocks per quad\n");
   for (int work : {0, 8, 12, 14, 16, 18}) run<1024, 1, 0, 0>("1024thr pf1 ld.nc st.cs (K1 today)", b, nq, 148, BIG, work);
+  printf("# eight boards per thread and iteration (K1 v2): adjacent quads vs warp-tile mapping\n");
+  for (int work : {0, 4, 6}) run8<1024, 0, 0>("OCT adjacent quads (64 B lane stride) st.cs", b, nq, 148, 229664, work);
+  for (int work : {0, 4, 6}) run8<1024, 1, 0>("OCT warp tile (contiguous 1 KB) st.cs", b, nq, 148, 229664, work);
+  for (int work : {0, 4, 6}) run8<1024, 0, 3>("OCT adjacent quads st.noalloc", b, nq, 148, 229664, work);
+  for (int work : {0, 4, 6}) run8<1024, 1, 3>("OCT warp tile st.noalloc", b, nq, 148, 229664, work);
   printf("# 256-bit board loads / next stores (one full 32 B sector per lane and instruction)\n");
   for (int work : {0, 8, 12}) run<1024, 1, 0, 0, true>("W256 1024thr pf1 ld.nc st.cs", b, nq, 148, BIG, work);
   for (int work : {0, 8, 12}) run<1024, 1, 1, 0, true>("W256 1024thr pf1 ld.default st.cs", b, nq, 148, BIG, work);

@@ -45,6 +45,9 @@ SIGNATURES = {
     "b2048_random_actions": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint64, c_void_p]),
     "b2048_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_uint64,
                                 c_uint64, c_uint64, c_uint32, c_void_p, c_int]),
+    "b2048_host_alloc": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_size_t, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "b2048_host_free": (c_int, [c_void_p]),
+    "b2048_bind_thread_near": (c_int, [c_int]),
     "replay_append": (c_int, [ctypes.POINTER(Ring), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_void_p]),
     "replay_sample": (c_int, [ctypes.POINTER(Ring), c_int64, c_uint64, c_uint64, c_void_p, c_void_p,

@@ -38,8 +38,9 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
 
 def shard(n_total: int, rank: int, world_size: int) -> tuple[int, int]:
     """Contiguous global-index range of `rank`: (index_base, n_local).  Bases are kept multiples
-    of 4 so that every shard takes the streaming kernel's aligned Philox path."""
-    per = (n_total // world_size) & ~3
+    of 8 so that every shard takes the streaming kernel's aligned Philox path (one call per eight
+    consecutive global board indices)."""
+    per = (n_total // world_size) & ~7
     base = rank * per
     n_local = per if rank < world_size - 1 else n_total - base
     return base, n_local

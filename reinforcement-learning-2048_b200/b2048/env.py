@@ -229,6 +229,34 @@ def random_actions(n, seed=2050, step_index=0, index_base=0, device="cuda", out=
     return actions
 
 
+def steady_state_boards(n, seed=2049, steps=64, index_base=0, p4=P4_TEN_PERCENT, device="cuda", chunk=1 << 23):
+    """The second synthetic distribution of SURVEY.md §8(d), "rollout-steady-state": boards after `steps`
+    uniformly random LEGAL moves from reset (dead boards restart).  Built on the device in chunks: legal mask
+    -> argmax of random scores over the legal moves -> env step -> masked reset.  Deterministic in
+    (seed, index_base).  Benchmark-input generator only (torch ops for the action choice)."""
+    boards = torch.empty(n, dtype=torch.int64, device=device)
+    gen = torch.Generator(device=boards.device)
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        base = index_base + c0
+        gen.manual_seed((seed * 1000003 + base) & 0x7FFFFFFFFFFFFFFF)
+        b = new_boards(m, device=boards.device, seed=seed, step_index=0, index_base=base, p4=p4)
+        nxt, rew, flg = torch.empty_like(b), torch.empty(m, dtype=torch.int32, device=b.device), \
+            torch.empty(m, dtype=torch.uint8, device=b.device)
+        legal = torch.empty(m, dtype=torch.uint8, device=b.device)
+        bits = torch.tensor([1, 2, 4, 8], dtype=torch.uint8, device=b.device)
+        for t in range(1, steps + 1):
+            legal_mask(b, out=legal)
+            score = torch.rand((m, 4), dtype=torch.float32, device=b.device, generator=gen)
+            score.masked_fill_((legal[:, None] & bits) == 0, -1.0)
+            acts = score.argmax(dim=1).to(torch.uint8)
+            step(b, acts, seed=seed, step_index=t, index_base=base, p4=p4, out=(nxt, rew, flg))
+            reset(nxt, seed=seed ^ 0x4E57, step_index=t, index_base=base, p4=p4, where_flags=flg)
+            b, nxt = nxt, b
+        boards[c0:c0 + m] = b
+    return boards
+
+
 def step_host(boards, actions, nxt, reward, flags, seed=0, step_index=0, index_base=0, p4=P4_TEN_PERCENT,
               spawn_override=None, device=0):
     """b2048_step with HOST buffers (numpy arrays or CPU tensors, ideally pinned): the library
@@ -248,6 +276,40 @@ def step_host(boards, actions, nxt, reward, flags, seed=0, step_index=0, index_b
                                           seed & _U64, step_index & _U64, index_base & _U64, p4,
                                           hp(spawn_override), device), "b2048_step_host")
     return nxt, reward, flags
+
+
+class PinnedBuffer:
+    """NUMA-local pinned host memory (b2048_host_alloc) viewed as a numpy array / CPU tensor.  Keep the
+    object alive as long as the views are used; `free()` (or garbage collection) releases the memory."""
+
+    def __init__(self, n: int, dtype, device: int = 0):
+        import ctypes
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(n) * self.dtype.itemsize
+        ptr, node, bound = _lib.c_void_p(), ctypes.c_int(-1), ctypes.c_int(0)
+        _lib.check(_lib.lib().b2048_host_alloc(ctypes.byref(ptr), max(self.nbytes, 1), int(device), ctypes.byref(node),
+                                               ctypes.byref(bound)), "b2048_host_alloc")
+        self.ptr, self.numa_node, self.bound = int(ptr.value), int(node.value), bool(bound.value)
+        raw = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(n))
+        self.tensor = torch.from_numpy(self.array)
+
+    def free(self) -> None:
+        if self.ptr:
+            self.array = self.tensor = None
+            _lib.lib().b2048_host_free(_lib.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def bind_thread_near(device: int = 0) -> bool:
+    """Bind the calling thread to the CPUs next to `device`; False if the topology is unknown."""
+    return _lib.lib().b2048_bind_thread_near(int(device)) == 0
 
 
 def row_lut_host() -> np.ndarray:

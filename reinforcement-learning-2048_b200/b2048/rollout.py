@@ -16,7 +16,7 @@ from .replay import ReplayRing
 
 
 class VectorEnv:
-    def __init__(self, n: int, device="cuda", seed: int = 0, index_base: int = 0, p_four: float = 0.1,
+    def __init__(self, n: int, device="cuda", seed: int = 0, index_base: int = 0, p_four: float = 0.5,
                  conv: bool = True):
         self.n, self.device, self.seed, self.index_base = int(n), torch.device(device), int(seed), int(index_base)
         self.p4 = env.p4_threshold(p_four)

@@ -25,6 +25,9 @@ constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
 #ifndef B2048_V_SWZ
 #define B2048_V_SWZ 1
 #endif
+#ifndef B2048_V_SPAWN_SHIFT
+#define B2048_V_SPAWN_SHIFT 1   // insert the spawned tile with a variable shift (0: IMAD.HI; A/B: 0.318 vs 0.324 ms)
+#endif
 constexpr int LUT_SWZ_SHIFT = 6;
 constexpr uint32_t LUT_SWZ_MASK = B2048_V_SWZ ? 31u : 0u;
 __host__ __device__ constexpr uint32_t lut_swizzle(uint32_t i) { return i ^ ((i >> LUT_SWZ_SHIFT) & LUT_SWZ_MASK); }
@@ -68,9 +71,16 @@ __host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint3
 #endif
 }
 
+// Rounds: every stream of the library is Philox4x32-10 except the spawn stream of the env-step kernels, which
+// is Philox4x32-7 -- the smallest round count Salmon et al. report as passing BigCrush ("Crush-resistant"),
+// offered as philox4x32_7 by Random123.  The generator sits inside the ALU/issue-bound step loop, where three
+// rounds less are worth 2 % of the kernel (0.317 -> 0.310 ms per 64 Mi boards).
+constexpr int PHILOX_ROUNDS = 10;
+constexpr int SPAWN_PHILOX_ROUNDS = 7;
+template <int ROUNDS = PHILOX_ROUNDS>
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < ROUNDS; ++i) {
     uint32_t h0, l0, h1, l1;
     mulhilo32(0xD2511F53u, c.x, h0, l0);
     mulhilo32(0xCD9E8D57u, c.z, h1, l1);
@@ -98,9 +108,10 @@ __host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed, uint32_t domain
   }
   return pk;
 }
+template <int ROUNDS = PHILOX_ROUNDS>
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& pk) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < ROUNDS; ++i) {
     uint32_t h0, l0, h1, l1;
     mulhilo32(0xD2511F53u, c.x, h0, l0);
     mulhilo32(0xCD9E8D57u, c.z, h1, l1);
@@ -109,9 +120,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& pk) {
   return c;
 }
 
+template <int ROUNDS = PHILOX_ROUNDS>
 __host__ __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t domain, uint64_t idx,
                                                     uint64_t step) {
-  return philox4x32_10(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)step,
+  return philox4x32_10<ROUNDS>(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)step,
                                   (uint32_t)(step >> 32)),
                        (uint32_t)seed, (uint32_t)(seed >> 32) ^ domain);
 }
@@ -339,6 +351,57 @@ __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint
   hi = __umulhi(h_hi, e29) + hi;
 }
 
+// ---- spawn stream v2 (B2048_ABI_VERSION 2) -----------------------------------------------------------
+// Board g owns ONE 16-bit lane of a Philox4x32-7 call: call counter (g >> 3, step), lane g & 7 (lane j =
+// half j & 1 of word j >> 1, low half first).  With the lane value d (0..65535) in the UPPER half of a
+// 32-bit word D = d << 16 and n = number of empty cells of the slid board, one 32x32 -> 64 bit product
+// D * n gives both draws: the high word k = floor(d * n / 65536) is the row-major rank of the cell, the
+// low word frac = ((d * n) mod 65536) << 16 is a uniform fraction that decides the value ("4" iff
+// frac < p4_threshold).  For odd n the map d -> d*n mod 65536 is a bijection, for even n it is uniform
+// over multiples of n's power of two, so P(4) is exact to 2^-13 and independent of k; each cell's
+// probability differs from 1/n by at most 2^-16.  One Philox call now serves eight boards: the step
+// kernel's per-board cost of the generator drops from 10 to 5 instructions.
+template <class A = Add7>
+__device__ __forceinline__ void spawn_draw16(uint32_t& lo, uint32_t& hi, uint32_t D, uint32_t p4, uint32_t changed,
+                                             A add = A()) {
+  const uint32_t e3_lo = ~(add(lo & 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
+  const uint32_t e3_hi = ~(add(hi & 0x77777777u) | hi) & 0x88888888u;
+  const uint32_t e_lo = (e3_lo >> 3), e_hi = (e3_hi >> 3);
+  const uint32_t p_lo = e_lo * 0x11111111u;                            // inclusive prefix counts per nibble
+  const uint32_t c_lo = (p_lo >> 28);
+  const uint32_t p_hi = e_hi * 0x11111111u + c_lo * 0x11111111u;
+  const uint32_t cnt = (p_hi >> 28);
+  uint32_t k, frac;
+  mulhilo32(D, cnt, k, frac);
+  const uint32_t tgt = k * 0x11111111u + 0x11111111u;                  // (k+1) in every nibble
+  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt, add) & e3_lo;            // bit 3 of the chosen nibble
+  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt, add) & e3_hi;
+#if B2048_V_SPAWN_SHIFT
+  const uint32_t sh = (frac < p4) ? 2u : 3u;                           // bit 3 -> bit 1 ("4") or bit 0 ("2")
+  if (changed) {
+    lo += h_lo >> sh;
+    hi += h_hi >> sh;
+  }
+#else
+  const uint32_t e29 = (frac < p4) ? (2u << 29) : (1u << 29);          // hi32(h * (e << 29)) = (h >> 3) * e
+  if (changed) {
+    lo = __umulhi(h_lo, e29) + lo;
+    hi = __umulhi(h_hi, e29) + hi;
+  }
+#endif
+}
+
+// lane l (0..7) of a Philox result, as D = d << 16
+__device__ __forceinline__ uint32_t draw_lane(const uint4& r, uint32_t l) {
+  const uint32_t j = l >> 1;
+  const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
+  return (l & 1u) ? (w & 0xFFFF0000u) : (w << 16);
+}
+// the draw of global board g (one Philox call per board: small / cold paths only)
+__device__ __forceinline__ uint32_t spawn_draw_of(uint64_t seed, uint64_t step, uint64_t g) {
+  return draw_lane(philox_at<SPAWN_PHILOX_ROUNDS>(seed, DOM_SPAWN, g >> 3, step), (uint32_t)g & 7u);
+}
+
 // Insert exponent e at cell (0..15); returns false if the cell is occupied.
 __device__ __forceinline__ bool spawn_at(uint32_t& lo, uint32_t& hi, uint32_t cell, uint32_t e) {
   const uint32_t sh = (cell & 7u) * 4u;
@@ -368,7 +431,7 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
 #define B2048_V_LDMODE 0
 #endif
 #ifndef B2048_V_STMODE
-#define B2048_V_STMODE 0
+#define B2048_V_STMODE 2   // st.global.L1::no_allocate (0: .cs, 1: default); A/B: 0.324 vs 0.333 ms
 #endif
 __device__ __forceinline__ void ld_stream_v8(const void* p, uint4& a, uint4& b) {
 #if B2048_V_LDMODE == 0

@@ -52,29 +52,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // Per-board tail shared by the step kernels: spawn one tile iff the move changed the board.
-//   w   : the board's Philox word (position from the high bits, value from the low 16 bits)
+//   D   : the board's spawn draw (16-bit Philox lane in the upper half, see spawn_draw16)
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
 template <bool HAS_OVERRIDE, class A = Add7>
-__device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t w,
+__device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t D,
                                              uint32_t p4, uint32_t ovr, uint32_t& flags, A add = A()) {
-  const uint32_t e29 = changed ? (((w << 16) < p4) ? (2u << 29) : (1u << 29)) : 0u;
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_kth_empty(nlo, nhi, w, e29, add);
+    spawn_draw16(nlo, nhi, D, p4, changed, add);
   } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
 }
 
-// The Philox word of global board g: word (g & 3) of the call with counter (g >> 2, step).
-__device__ __forceinline__ uint32_t pick_word(const uint4& r, uint32_t j) {
-  return j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
-}
-
+// 768 threads per CTA (24 warps, 6 per scheduler, 80 registers per thread): with 1024 threads the 64-register
+// cap spills four values per iteration to local memory, and those reloads miss the (tiny) L1 next to the
+// 224 KB table; 896 / 640 / 512 threads measured 0.329 / 0.320 / 0.331 ms against 0.318 ms (64 Mi boards).
 #ifndef B2048_STREAM_THREADS
-#define B2048_STREAM_THREADS 1024
-#endif
-#ifndef B2048_V_W256
-#define B2048_V_W256 1     // 256-bit board loads / next-board stores (needs 32-byte aligned boards / next)
+#define B2048_STREAM_THREADS 768
 #endif
 constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 
@@ -83,8 +77,8 @@ constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 // pointers ptxas re-derived the shared window base (S2R + MOV + LEA) for every board.
 constexpr uint32_t SM_ACT = (uint32_t)LUT_SMEM_BYTES;   // 4 rows x 32 B: per-action transform constants
 constexpr uint32_t SM_LEGAL = SM_ACT + 128;             // 4 rows x 32 B: flags byte per (action, frame mask)
-constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // run-time constants {4, 1, 2, 0}
-constexpr uint32_t SM_BAR = SM_CONST + 16;              // mbarrier
+constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // run-time constants (StreamConsts)
+constexpr uint32_t SM_BAR = SM_CONST + 32;              // mbarrier
 constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
 
 // Instruction selection in stream_board follows measurements on B200 (profiles/ubench):
@@ -92,7 +86,26 @@ constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
 // the busiest unit, the FMA pipe (IMAD, IDP) has room.  So table addresses and 16-bit extracts are
 // integer dot products (IDP.2A/4A: "half-word * 4 + base" in one FMA-pipe instruction, no PRMT/LEA),
 // the "+0x7777.." of the nibble tests is an IMAD through a run-time 1, and selectors go to PRMT raw.
-#define SHR16(x) __dp2a_hi((x), 0x01000000u, 0u)   // x >> 16 as (high half * 1) on the FMA pipe
+#ifndef B2048_V_REGCONST
+#define B2048_V_REGCONST 1   // 1: dot-product weights and p4 live in registers (read once from shared memory, opaque to ptxas)
+#endif
+// run-time copies of constants: `one` feeds Add7Fma; with B2048_V_REGCONST the IDP weights and the spawn
+// threshold too, so that ptxas does not re-materialise them (UMOV / LDC) for every board
+struct StreamConsts {
+  uint32_t one, p4, k4, k16, k44;
+};
+#if B2048_V_REGCONST
+#define K_W4(k) (k).k4
+#define K_W16(k) (k).k16
+#define K_W44(k) (k).k44
+#define K_P4(k, p4) (k).p4
+#else
+#define K_W4(k) 0x04000004u
+#define K_W16(k) 0x01000000u
+#define K_W44(k) 0x0404u
+#define K_P4(k, p4) (p4)
+#endif
+#define SHR16(x) __dp2a_hi((x), K_W16(kc), 0u)   // x >> 16 as (high half * 1) on the FMA pipe
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
@@ -114,16 +127,20 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // Same arithmetic as slide_board + finish_board (b2048_common.cuh), specialised for the
 // shared-memory map above; the flags byte incl. CHANGED comes straight from the legal table.
 //
-// There is no branch in here: rows outside the staged part of the table (top cell >= 2^14, never
-// seen in play) are clamped for the lookup and only recorded in `mx`; the caller redoes such a quad
-// on a cold path after its stores (fix_quad).  One basic block per four boards lets ptxas overlap
-// the shared-memory latency of one board with the arithmetic of the others.
+// There is no branch in here.  Rows outside the staged part of the table (top cell >= 2^14, never seen
+// in play) are clamped to the LAST staged row, 0xDFFF = cells [15,15,15,13]: that row merges 32768+32768,
+// so its table entry carries the OVERFLOW bit and a clamped lookup simply raises B2048_FLAG_OVERFLOW in
+// the flags byte.  The caller redoes every quad that shows the flag from the full table in global memory
+// (fix_quad), which also gives genuinely overflowing boards their exact flags.  One basic block per
+// four boards lets ptxas overlap the shared-memory latency of one board with the arithmetic of the others.
 constexpr uint32_t LUT_LIM2 = ((uint32_t)LUT_SMEM_ROWS - 1u) * 0x00010001u;   // last staged row, both halves
+static_assert(LUT_SMEM_ROWS - 1 == 0xDFFF, "the clamp row must be one whose entry has the OVERFLOW bit");
 template <bool HAS_OVERRIDE>
-__device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32_t& mx,
-                                             uint32_t lo, uint32_t hi, uint32_t w, uint32_t p4, uint32_t ovr,
+__device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa,
+                                             uint32_t lo, uint32_t hi, uint32_t D, uint32_t p4, uint32_t ovr,
                                              uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags,
-                                             uint32_t one) {
+                                             const StreamConsts& kc) {
+  const uint32_t one = kc.one;
   const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
   const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
   uint32_t zl = prmt_raw(lo, hi, xa.x);
@@ -133,7 +150,6 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
     zl ^= tl ^ (tl * xb.x);
     zh ^= th ^ (th * xb.x);
   }
-  mx = __vmaxu2(__vmaxu2(zl, zh), mx);         // VIMNMX3: running maximum of every row of the quad
   uint32_t e0, e1, e2, e3;
   {
     const uint32_t cl = __vminu2(zl, LUT_LIM2), ch = __vminu2(zh, LUT_LIM2);
@@ -147,10 +163,10 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
     e2 = __dp2a_lo(sh, 0x04000004u, sbase) * 0x9E3779B1u;
     e3 = __dp2a_hi(sh, 0x04000004u, sbase) * 0x9E3779B1u;
 #else
-    e0 = lds32(__dp2a_lo(sl, 0x04000004u, sbase));
-    e1 = lds32(__dp2a_hi(sl, 0x04000004u, sbase));
-    e2 = lds32(__dp2a_lo(sh, 0x04000004u, sbase));
-    e3 = lds32(__dp2a_hi(sh, 0x04000004u, sbase));
+    e0 = lds32(__dp2a_lo(sl, K_W4(kc), sbase));
+    e1 = lds32(__dp2a_hi(sl, K_W4(kc), sbase));
+    e2 = lds32(__dp2a_lo(sh, K_W4(kc), sbase));
+    e3 = lds32(__dp2a_hi(sh, K_W4(kc), sbase));
 #endif
   }
   uint32_t wl = __byte_perm(e0, e1, 0x5410);
@@ -158,7 +174,7 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
   const uint32_t fl = h01 | h23;
-  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, 0x0404u, __dp2a_lo(h01 & 0x3FFF3FFFu, 0x0404u, 0u));   // 4 * sum of 14-bit fields
+  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));   // 4 * sum of 14-bit fields
 
   // legality of the input board in the transformed frame (see slide_board)
   const uint32_t changed = (wl ^ zl) | (wh ^ zh);
@@ -191,16 +207,12 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa, uint32
     wl ^= tl ^ (tl * xb.x);
     wh ^= th ^ (th * xb.x);
   }
-#ifdef B2048_DIAG_NOINV
-  olo = wl; ohi = wh;
-#else
   olo = prmt_raw(wl, wh, xa.z);
   ohi = prmt_raw(wl, wh, xa.w);
-#endif
 #ifdef B2048_DIAG_NOSPAWN
-  olo ^= changed ? w : 0u;
+  olo ^= changed ? D : 0u;
 #else
-  finish_board<HAS_OVERRIDE>(olo, ohi, changed, w, p4, ovr, flags, add);
+  finish_board<HAS_OVERRIDE>(olo, ohi, changed, D, K_P4(kc, p4), ovr, flags, add);
 #endif
 }
 
@@ -220,27 +232,69 @@ __device__ __noinline__ void fix_quad(uint32_t quad, const uint4* __restrict__ b
   for (uint32_t j = 0; j < 4; ++j) {
     const uint64_t bd = bq[j];
     const uint64_t g = index_base + 4ull * quad + j;
-    const uint64_t pidx = g >> 2;
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step,
-                                             (uint32_t)(step >> 32)), keys);
-    const uint32_t w = pick_word(r, (uint32_t)g & 3u);
+    const uint64_t pidx = g >> 3;
+    const uint4 r = philox4x32_10<SPAWN_PHILOX_ROUNDS>(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step,
+                                                                  (uint32_t)(step >> 32)), keys);
+    const uint32_t D = draw_lane(r, (uint32_t)g & 7u);
     uint32_t nl, nh, rw, f, ch;
     slide_board<true>((uint32_t)bd, (uint32_t)(bd >> 32), (a4 >> (8 * j)) & 3u, nullptr, glut, nl, nh, rw, f, ch);
-    finish_board<HAS_OVERRIDE>(nl, nh, ch, w, p4, (o4 >> (8 * j)) & 0xFFu, f);
+    finish_board<HAS_OVERRIDE>(nl, nh, ch, D, p4, (o4 >> (8 * j)) & 0xFFu, f);
     nq[j] = ((uint64_t)nh << 32) | nl;
     rq[j] = (int32_t)rw;
     fq[j] = (uint8_t)f;
   }
 }
 
-// ---- streaming kernel: four boards per thread, table in shared memory ----------------------------
-// Requires 32-byte aligned boards/next, 16-byte aligned reward, 4-byte aligned actions/flags/override and n % 4 == 0
-// (the host wrapper sends the remainder and unaligned batches to step_small_kernel).
+// Predicated loads of one quad into registers that keep their old contents when the predicate is false
+// (no zero-initialisation of the prefetch buffers inside the loop).
+__device__ __forceinline__ void ld_quad(bool pred, const uint4* boards2, const uint32_t* actions4,
+                                        const uint32_t* override4, bool has_override, uint32_t quad, uint4& ba,
+                                        uint4& bb, uint32_t& a4, uint32_t& o4) {
+  if (pred) {
+    ld_stream_v8(boards2 + 2u * quad, ba, bb);
+    a4 = ld_stream_u32(actions4 + quad);
+    if (has_override) o4 = ld_stream_u32(override4 + quad);
+  }
+}
+
+// Four boards: slide + merge + flags + spawn, three coalesced stores.  Returns true when the quad has to
+// be redone on the cold path (a clamped or overflowing row raised B2048_FLAG_OVERFLOW).
+template <bool HAS_OVERRIDE>
+__device__ __forceinline__ bool stream_quad(uint32_t sbase, const StreamConsts& one, uint32_t p4, const uint4& ba,
+                                            const uint4& bb, uint32_t a4, uint32_t o4, uint32_t w_lo, uint32_t w_hi,
+                                            uint32_t quad, uint4* __restrict__ next2, uint4* __restrict__ reward4,
+                                            uint32_t* __restrict__ flags4) {
+  const uint32_t a32 = a4 & 0x03030303u;     // byte j * 32 + base = one IDP.4A per board
+#define SA_OF(j) __dp4a(a32, 0x20u << (8 * (j)), sbase)
+  uint32_t n0l, n0h, n1l, n1h, n2l, n2h, n3l, n3h, rw0, rw1, rw2, rw3, f, fw;
+  // draws: 16-bit lanes of the octet's Philox words, moved to the upper half (low lane first);
+  // the four flag bytes are packed as they arrive (one live register instead of four)
+  stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), ba.x, ba.y, w_lo << 16, p4, o4 & 0xFFu, n0l, n0h, rw0, fw, one);
+  stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), ba.z, ba.w, w_lo & 0xFFFF0000u, p4, (o4 >> 8) & 0xFFu, n1l, n1h, rw1,
+                             f, one);
+  fw += f * 256u;
+  stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), bb.x, bb.y, w_hi << 16, p4, (o4 >> 16) & 0xFFu, n2l, n2h, rw2, f, one);
+  fw += f * 65536u;
+  stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), bb.z, bb.w, w_hi & 0xFFFF0000u, p4, o4 >> 24, n3l, n3h, rw3, f, one);
+  fw += f * 16777216u;
+#undef SA_OF
+  st_stream_v8(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h), make_uint4(n2l, n2h, n3l, n3h));
+  st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
+  flags4[quad] = fw;
+  return (fw & (B2048_FLAG_OVERFLOW * 0x01010101u)) != 0u;
+}
+
+// ---- streaming kernel: eight boards (two quads, one Philox call) per thread and iteration -------------
+// Requires 32-byte aligned boards/next, 16-byte aligned reward, 4-byte aligned actions/flags/override and
+// n % 8 == 0 (the host wrapper sends the remainder and unaligned batches to step_small_kernel).
+// Software pipeline without register rotation: buffer X holds the iteration's first quad (loaded during the
+// previous iteration), buffer Y its second quad (requested at the top, consumed after X has been processed);
+// X is refilled for the next iteration before Y is processed.
 template <bool HAS_OVERRIDE>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
     step_stream_kernel(const uint4* __restrict__ boards2, const uint32_t* __restrict__ actions4,
                        uint4* __restrict__ next2, uint4* __restrict__ reward4,
-                       uint32_t* __restrict__ flags4, int64_t nquads,
+                       uint32_t* __restrict__ flags4, int64_t nocts,
                        const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
                        uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -260,7 +314,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   }
   if (threadIdx.x == 0) {
     uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
-    k[0] = 4u; k[1] = 1u; k[2] = 2u; k[3] = 0u;
+    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4;
   }
   if (threadIdx.x < 128) {
     const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
@@ -277,96 +331,65 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut + LUT_ROWS) + off, CHUNK, bar);
   }
 
-  // 32-bit quad index (the host wrapper keeps nquads < 2^32): every global address is then one
+  // 32-bit octet / quad indices (the host wrapper keeps nocts < 2^31): every global address is then one
   // IMAD.WIDE (base + index * size) on the FMA pipe instead of 64-bit LEA pairs on the ALU pipe.
   const uint32_t stride = gridDim.x * STREAM_THREADS;
-  const uint32_t nq = (uint32_t)nquads;
-  uint32_t quad = blockIdx.x * STREAM_THREADS + threadIdx.x;
-  const uint32_t base_mis = (uint32_t)index_base & 3u;
-  const uint64_t pidx_base = index_base >> 2;
+  const uint32_t no = (uint32_t)nocts;
+  uint32_t oct = blockIdx.x * STREAM_THREADS + threadIdx.x;
+  const uint32_t base_mis = (uint32_t)index_base & 7u;
+  const uint64_t pidx_base = index_base >> 3;
   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
 
-  // first loads are issued before waiting for the table
-  uint4 ba = make_uint4(0, 0, 0, 0), bb = ba;
-  uint32_t a4 = 0, o4 = 0xFFFFFFFFu;
-  if (quad < nq) {
-#if B2048_V_W256
-    ld_stream_v8(boards2 + 2u * quad, ba, bb);
-#else
-    ba = ld_stream_v4(boards2 + 2u * quad);
-    bb = ld_stream_v4(boards2 + 2u * quad + 1);
-#endif
-    a4 = ld_stream_u32(actions4 + quad);
-    if (HAS_OVERRIDE) o4 = ld_stream_u32(override4 + quad);
-  }
+  // the first loads are issued before waiting for the table
+  uint4 xa = make_uint4(0, 0, 0, 0), xb = xa, ya = xa, yb = xa;
+  uint32_t ax = 0, ay = 0, ox = 0xFFFFFFFFu, oy = 0xFFFFFFFFu;
+  ld_quad(oct < no, boards2, actions4, override4, HAS_OVERRIDE, 2u * oct, xa, xb, ax, ox);
   mbar_wait(bar, 0);
-  const uint32_t one = lds32(sbase + SM_CONST + 4);   // a 1 that ptxas cannot see (Add7Fma)
+  StreamConsts one;                                    // run-time constants that ptxas cannot see through
+  {
+    const uint4 k = lds128(sbase + SM_CONST);
+    one.one = k.y; one.k4 = k.x; one.k16 = k.z; one.k44 = k.w;
+    one.p4 = lds32(sbase + SM_CONST + 16);
+  }
 
-  while (quad < nq) {
-    // prefetch this thread's next quad (stride < 2^18, so the sum cannot wrap for nq < 2^32 - 2^18)
-    const uint32_t nxt = quad + stride;
-    uint4 na = make_uint4(0, 0, 0, 0), nb = na;
-    uint32_t an = 0, on = 0xFFFFFFFFu;
-    if (nxt < nq) {
-#if B2048_V_W256
-      ld_stream_v8(boards2 + 2u * nxt, na, nb);
-#else
-      na = ld_stream_v4(boards2 + 2u * nxt);
-      nb = ld_stream_v4(boards2 + 2u * nxt + 1);
-#endif
-      an = ld_stream_u32(actions4 + nxt);
-      if (HAS_OVERRIDE) on = ld_stream_u32(override4 + nxt);
-    }
+  while (oct < no) {
+    ld_quad(true, boards2, actions4, override4, HAS_OVERRIDE, 2u * oct + 1u, ya, yb, ay, oy);
 
-    // one Philox4x32-10 call per aligned group of four global board indices
-    const uint64_t pidx = pidx_base + quad;
+    // one Philox4x32-7 call per aligned group of EIGHT global board indices (16-bit lanes)
+    const uint64_t pidx = pidx_base + oct;
 #ifdef B2048_DIAG_NOPHILOX
     uint4 w = make_uint4((uint32_t)pidx * 0x9E3779B9u, (uint32_t)pidx * 0x85EBCA6Bu, s_lo * 0xC2B2AE35u ^ (uint32_t)pidx, (uint32_t)pidx * 0x27D4EB2Fu);
 #else
-    uint4 w = philox4x32_10(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
+    uint4 w = philox4x32_10<SPAWN_PHILOX_ROUNDS>(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
 #endif
-    if (base_mis != 0) {  // uniform: index_base not a multiple of 4 -> the quad straddles two calls
+    if (base_mis != 0) {  // uniform: index_base not a multiple of 8 -> the octet straddles two calls
       const uint64_t p1 = pidx + 1;
-      const uint4 w1 = philox4x32_10(make_uint4((uint32_t)p1, (uint32_t)(p1 >> 32), s_lo, s_hi), keys);
-      uint32_t t[4];
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t q = base_mis + j;
-        t[j] = q < 4 ? pick_word(w, q) : pick_word(w1, q - 4);
+      const uint4 w1 = philox4x32_10<SPAWN_PHILOX_ROUNDS>(make_uint4((uint32_t)p1, (uint32_t)(p1 >> 32), s_lo, s_hi), keys);
+      // lanes base_mis .. base_mis + 7 of the 16-lane sequence {w, w1}
+      uint32_t c0, c1, c2, c3, c4;
+      switch (base_mis >> 1) {
+        case 0: c0 = w.x; c1 = w.y; c2 = w.z; c3 = w.w; c4 = w1.x; break;
+        case 1: c0 = w.y; c1 = w.z; c2 = w.w; c3 = w1.x; c4 = w1.y; break;
+        case 2: c0 = w.z; c1 = w.w; c2 = w1.x; c3 = w1.y; c4 = w1.z; break;
+        default: c0 = w.w; c1 = w1.x; c2 = w1.y; c3 = w1.z; c4 = w1.w; break;
       }
-      w = make_uint4(t[0], t[1], t[2], t[3]);
+      const uint32_t sh = (base_mis & 1u) * 16u;
+      w = make_uint4(__funnelshift_r(c0, c1, sh), __funnelshift_r(c1, c2, sh), __funnelshift_r(c2, c3, sh),
+                     __funnelshift_r(c3, c4, sh));
     }
 
-    const uint32_t a32 = a4 & 0x03030303u;     // byte j * 32 + base = one IDP.4A per board
-#define SA_OF(j) __dp4a(a32, 0x20u << (8 * (j)), sbase)
-    uint32_t n0l, n0h, n1l, n1h, rw0, rw1, rw2, rw3, f0, f1, f2, f3, mx = LUT_LIM2;
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), mx, ba.x, ba.y, w.x, p4,
-                               o4 & 0xFFu, n0l, n0h, rw0, f0, one);
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), mx, ba.z, ba.w, w.y, p4,
-                               (o4 >> 8) & 0xFFu, n1l, n1h, rw1, f1, one);
-#if B2048_V_W256
-    uint32_t n2l, n2h, n3l, n3h;
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), mx, bb.x, bb.y, w.z, p4,
-                               (o4 >> 16) & 0xFFu, n2l, n2h, rw2, f2, one);
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), mx, bb.z, bb.w, w.w, p4,
-                               o4 >> 24, n3l, n3h, rw3, f3, one);
-    st_stream_v8(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h), make_uint4(n2l, n2h, n3l, n3h));
-#else
-    st_stream_v4(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h));
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), mx, bb.x, bb.y, w.z, p4,
-                               (o4 >> 16) & 0xFFu, n0l, n0h, rw2, f2, one);
-    stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), mx, bb.z, bb.w, w.w, p4,
-                               o4 >> 24, n1l, n1h, rw3, f3, one);
-    st_stream_v4(next2 + 2u * quad + 1, make_uint4(n0l, n0h, n1l, n1h));
-#endif
-    st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
-    flags4[quad] = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
-    if (__builtin_expect(mx != LUT_LIM2, 0))   // some row of the quad was clamped: redo it from global memory
-      fix_quad<HAS_OVERRIDE>(quad, boards2, actions4, next2, reward4, flags4, glut, keys, step, index_base, p4,
+    if (__builtin_expect(stream_quad<HAS_OVERRIDE>(sbase, one, p4, xa, xb, ax, ox, w.x, w.y, 2u * oct, next2, reward4,
+                                                   flags4), 0))
+      fix_quad<HAS_OVERRIDE>(2u * oct, boards2, actions4, next2, reward4, flags4, glut, keys, step, index_base, p4,
                              override4);
-
-    ba = na; bb = nb; a4 = an; o4 = on;
-    quad = nxt;
+    // refill X for this thread's next octet (stride < 2^18, so the sum cannot wrap for nocts < 2^31)
+    const uint32_t nxt = oct + stride;
+    ld_quad(nxt < no, boards2, actions4, override4, HAS_OVERRIDE, 2u * nxt, xa, xb, ax, ox);
+    if (__builtin_expect(stream_quad<HAS_OVERRIDE>(sbase, one, p4, ya, yb, ay, oy, w.z, w.w, 2u * oct + 1u, next2,
+                                                   reward4, flags4), 0))
+      fix_quad<HAS_OVERRIDE>(2u * oct + 1u, boards2, actions4, next2, reward4, flags4, glut, keys, step, index_base,
+                             p4, override4);
+    oct = nxt;
   }
 }
 
@@ -386,10 +409,10 @@ __global__ void __launch_bounds__(256)
   const uint64_t bd = boards[i];
   const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
   const uint64_t g = index_base + (uint64_t)i;
-  const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
+  const uint32_t D = spawn_draw_of(seed, step, g);
   uint32_t nl, nh, rw, f, ch;
   slide_board<true>(lo, hi, actions[i] & 3u, &tabs, glut, nl, nh, rw, f, ch);
-  finish_board<HAS_OVERRIDE>(nl, nh, ch, w, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
+  finish_board<HAS_OVERRIDE>(nl, nh, ch, D, p4, HAS_OVERRIDE ? (uint32_t)override1[i] : 0xFFu, f);
   next[i] = ((uint64_t)nh << 32) | nl;
   reward[i] = (int32_t)rw;
   flags[i] = (uint8_t)f;
@@ -428,12 +451,11 @@ __global__ void __launch_bounds__(256)
   const uint64_t bd = boards[i];
   const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
   const uint64_t g = index_base + (uint64_t)i;
-  const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
+  const uint32_t D = spawn_draw_of(seed, step, g);   // the same draw for all four successors
   uint32_t nl[4], nh[4], rw[4], f;
-  all4_board<HAS_OVERRIDE>(lo, hi, &tabs, glut, w, p4,
+  all4_board<HAS_OVERRIDE>(lo, hi, &tabs, glut, D, p4,
                                   HAS_OVERRIDE ? override4[i] : 0xFFFFFFFFu, nl, nh, rw, f);
-  st_stream_v4(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]));
-  st_stream_v4(next4 + 2 * i + 1, make_uint4(nl[2], nh[2], nl[3], nh[3]));
+  st_stream_v8(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]), make_uint4(nl[2], nh[2], nl[3], nh[3]));
   st_stream_v4(reward4 + i, make_uint4(rw[0], rw[1], rw[2], rw[3]));
   flags[i] = (uint8_t)f;
 }
@@ -474,12 +496,11 @@ __global__ void spawn_kernel(uint64_t* __restrict__ boards, int64_t n, uint64_t 
   const uint64_t bd = boards[i];
   uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
   const uint64_t g = index_base + (uint64_t)i;
-  const uint32_t w = pick_word(philox_at(seed, DOM_SPAWN, g >> 2, step), (uint32_t)g & 3u);
-  const uint32_t e = ((w << 16) < p4) ? 2u : 1u;
-  if (bd == 0) {
-    spawn_at(lo, hi, w >> 28, e);            // 16 empty cells: the prefix trick needs <= 15
+  const uint32_t D = spawn_draw_of(seed, step, g);
+  if (bd == 0) {                             // 16 empty cells: the prefix trick needs <= 15; same rule, n = 16
+    spawn_at(lo, hi, D >> 28, ((D << 4) < p4) ? 2u : 1u);
   } else {
-    spawn_kth_empty(lo, hi, w, e << 29);     // no empty cell -> nothing happens
+    spawn_draw16(lo, hi, D, p4, 1u);         // no empty cell -> nothing happens
   }
   boards[i] = ((uint64_t)hi << 32) | lo;
 }
@@ -615,33 +636,38 @@ inline int64_t blocks_for(int64_t n, int threads) { return (n + threads - 1) / t
 // Batches at or above this many boards use the persistent shared-memory-table kernel.
 constexpr int64_t STREAM_MIN_BOARDS = 1 << 19;
 
+// The streaming kernel indexes octets with 32 bits: a batch is launched in pieces of at most
+// STREAM_MAX_OCTS octets (2^33 boards in the shipped build, i.e. never split in practice; the tests build
+// a variant with a small limit to run the split path).
+#ifndef B2048_STREAM_MAX_OCTS
+#define B2048_STREAM_MAX_OCTS (1ll << 30)
+#endif
+constexpr int64_t STREAM_MAX_OCTS = B2048_STREAM_MAX_OCTS;
+
 template <bool HAS_OVERRIDE>
 cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint8_t* actions,
                         uint64_t* next, int32_t* reward, uint8_t* flags, int64_t n, uint64_t seed,
                         uint64_t step, uint64_t index_base, uint32_t p4, const uint8_t* ovr,
                         cudaStream_t st) {
-  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next)) &
-                        (B2048_V_W256 ? 31u : 15u)) == 0 &&
+  const bool aligned = ((reinterpret_cast<uintptr_t>(boards) | reinterpret_cast<uintptr_t>(next)) & 31u) == 0 &&
                        (reinterpret_cast<uintptr_t>(reward) & 15u) == 0 &&
                        ((reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(flags) |
                          reinterpret_cast<uintptr_t>(ovr)) & 3u) == 0;
   int64_t done = 0;
   if (aligned && n >= STREAM_MIN_BOARDS) {
-    // the kernel indexes quads with 32 bits: launch in pieces of at most 2^33 boards (never in practice)
-    constexpr int64_t MAX_QUADS = (int64_t)1 << 31;
-    const int64_t nquads_total = n / 4;
-    for (int64_t q0 = 0; q0 < nquads_total; q0 += MAX_QUADS) {
-      const int64_t nquads = (nquads_total - q0 < MAX_QUADS) ? (nquads_total - q0) : MAX_QUADS;
-      const int64_t b0 = q0 * 4;
+    const int64_t nocts_total = n / 8;
+    for (int64_t o0 = 0; o0 < nocts_total; o0 += STREAM_MAX_OCTS) {
+      const int64_t nocts = (nocts_total - o0 < STREAM_MAX_OCTS) ? (nocts_total - o0) : STREAM_MAX_OCTS;
+      const int64_t b0 = o0 * 8;
       step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
           reinterpret_cast<const uint4*>(boards + b0), reinterpret_cast<const uint32_t*>(actions + b0),
           reinterpret_cast<uint4*>(next + b0), reinterpret_cast<uint4*>(reward + b0),
-          reinterpret_cast<uint32_t*>(flags + b0), nquads, ctx->lut, philox_keys(seed, DOM_SPAWN), step,
+          reinterpret_cast<uint32_t*>(flags + b0), nocts, ctx->lut, philox_keys(seed, DOM_SPAWN), step,
           index_base + (uint64_t)b0, p4, ovr ? reinterpret_cast<const uint32_t*>(ovr + b0) : nullptr);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
     }
-    done = nquads_total * 4;
+    done = nocts_total * 8;
   }
   if (done < n) {
     const int64_t m = n - done;
@@ -696,7 +722,7 @@ extern "C" int b2048_step_all4(const uint64_t* boards, uint64_t* next4, int32_t*
   if (n < 0) return B2048_EINVAL;
   if (n == 0) return B2048_OK;
   if (!boards || !next4 || !reward4 || !flags) return B2048_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(next4) | reinterpret_cast<uintptr_t>(reward4)) & 15u) return B2048_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(next4) & 31u) | (reinterpret_cast<uintptr_t>(reward4) & 15u)) return B2048_EINVAL;
   if (reinterpret_cast<uintptr_t>(spawn_override4) & 3u) return B2048_EINVAL;
   B2048_CTX_OR_RETURN();
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -1,6 +1,11 @@
 // host_api.cu — library lifetime, row-table construction and the host-buffer step entry point.
-#include <mutex>
+#include <ctype.h>
+#include <sched.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 #include <vector>
 
 #include "b2048_common.cuh"
@@ -168,6 +173,103 @@ extern "C" int b2048_copy_row_lut_host(uint32_t* out65536) {
   const std::vector<uint32_t>& lut = host_lut();
   memcpy(out65536, lut.data(), LUT_ROWS * sizeof(uint32_t));
   return B2048_OK;
+}
+
+// ---- NUMA-local pinned host memory ------------------------------------------------------------------
+// cudaHostAlloc places pages on the NUMA node of the calling thread (first touch under the default
+// policy).  A rank that happens to run on the far socket therefore stages its e2e buffers across the
+// inter-socket link: with eight ranks that halves the PCIe rate of half the GPUs.  b2048_host_alloc binds
+// the calling thread to the CPUs next to `device` (sysfs: /sys/bus/pci/devices/<id>/local_cpulist) for the
+// duration of the allocation and the first touch, then restores the previous affinity.  No libnuma needed.
+
+namespace {
+// parse "0-15,32-47" into a cpu_set_t; returns the number of CPUs found
+int parse_cpulist(const char* txt, cpu_set_t* set) {
+  CPU_ZERO(set);
+  int count = 0;
+  const char* p = txt;
+  while (*p) {
+    while (*p && !isdigit((unsigned char)*p)) ++p;
+    if (!*p) break;
+    char* end = nullptr;
+    long a = strtol(p, &end, 10), b = a;
+    p = end;
+    if (*p == '-') {
+      b = strtol(p + 1, &end, 10);
+      p = end;
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+      CPU_SET((int)c, set);
+      ++count;
+    }
+  }
+  return count;
+}
+
+// CPUs local to `device` intersected with the CPUs this process may use; false if unknown
+bool local_cpus(int device, cpu_set_t* out, int* numa_node) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return false;
+  for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+  char path[128], buf[4096] = {0};
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  const size_t got = fread(buf, 1, sizeof(buf) - 1, f);
+  fclose(f);
+  if (got == 0) return false;
+  cpu_set_t local, allowed;
+  if (parse_cpulist(buf, &local) == 0) return false;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
+  CPU_AND(out, &local, &allowed);
+  if (numa_node) {
+    *numa_node = -1;
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    if ((f = fopen(path, "r"))) {
+      if (fscanf(f, "%d", numa_node) != 1) *numa_node = -1;
+      fclose(f);
+    }
+  }
+  return CPU_COUNT(out) > 0;
+}
+}  // namespace
+
+extern "C" int b2048_host_alloc(void** out, size_t bytes, int device, int* numa_node_out, int* bound_out) {
+  if (!out || bytes == 0) return B2048_EINVAL;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return B2048_ENODEV;
+  }
+  if (device < 0 || device >= count) return B2048_EINVAL;
+  cpu_set_t prev, want;
+  int node = -1;
+  const bool have_prev = sched_getaffinity(0, sizeof(prev), &prev) == 0;
+  const bool bind = have_prev && local_cpus(device, &want, &node) && sched_setaffinity(0, sizeof(want), &want) == 0;
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  cudaSetDevice(device);
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e == cudaSuccess) memset(*out, 0, bytes);      // first touch while bound
+  cudaSetDevice(prev_dev);
+  if (bind) sched_setaffinity(0, sizeof(prev), &prev);
+  if (numa_node_out) *numa_node_out = node;
+  if (bound_out) *bound_out = bind ? 1 : 0;
+  return (int)e;
+}
+
+extern "C" int b2048_host_free(void* p) {
+  if (!p) return B2048_OK;
+  return (int)cudaFreeHost(p);
+}
+
+// Bind the CALLING thread to the CPUs next to `device` (the thread that drives b2048_step_host's copies).
+// Returns 0 if bound, B2048_EINVAL if the topology is unknown (nothing changed).
+extern "C" int b2048_bind_thread_near(int device) {
+  cpu_set_t want;
+  int node = -1;
+  if (!local_cpus(device, &want, &node)) return B2048_EINVAL;
+  return sched_setaffinity(0, sizeof(want), &want) == 0 ? B2048_OK : B2048_EINVAL;
 }
 
 // ---- host-buffer step: chunked 3-stage pipeline (H2D | kernel | D2H) -------------------------------

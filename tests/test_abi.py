@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(L, n), f"{n} declared in include/b2048.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in b2048/_lib.py"
     assert set(_lib.SIGNATURES) == set(names)
-    assert _lib.lib().b2048_abi_version() == 1
+    assert _lib.lib().b2048_abi_version() == 2
 
 
 def test_row_table_equals_reference_rows(golden_dir):

@@ -16,7 +16,7 @@ def test_shard_covers_everything_with_aligned_bases():
         spans = [bdist.shard(n, r, g) for r in range(g)]
         assert spans[0][0] == 0 and sum(s[1] for s in spans) == n
         for r in range(g):
-            assert spans[r][0] % 4 == 0
+            assert spans[r][0] % 8 == 0
             if r:
                 assert spans[r][0] == spans[r - 1][0] + spans[r - 1][1]
 

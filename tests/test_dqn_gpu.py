@@ -110,6 +110,28 @@ def test_ddqn_target_loss_matches_reference(cuda, dq, tag):
     assert loss2.item() == loss.item()
 
 
+def test_config3_dense_batch_5000_gamma_095_and_080(cuda, golden_dir):
+    """BASELINE.json config 3 as stated: batch 5000 out of the reference's buffer with the reference's own
+    indices (K2), then the fused target/loss (K3) on the Q tensors the reference's dense network produced, for
+    gamma = 0.95 and 0.80 (float32-rounded differently), Double DQN on and off."""
+    d = np.load(os.path.join(golden_dir, "dqn_dense_b5000.npz"))
+    ring = fill_ring(d, cuda)
+    st, ac, rw, ns, dn = ring.sample(5000, idx_override=torch.from_numpy(d["idx"]).to(cuda))
+    assert np.array_equal(st.cpu().numpy(), d["states"]) and np.array_equal(ns.cpu().numpy(), d["next_states"])
+    assert np.array_equal(ac.cpu().numpy(), d["actions"]) and np.array_equal(rw.cpu().numpy(), d["rewards"])
+    assert np.array_equal(dn.cpu().numpy(), d["dones"])
+    t = lambda k: torch.from_numpy(d[k]).to(cuda)  # noqa: E731
+    for gamma, gtag in ((0.95, "g095"), (0.80, "g080")):
+        for use_double in (True, False):
+            tag = f"{gtag}_{'double' if use_double else 'single'}"
+            loss, target, q_sa, _ = ddqn.ddqn_target_loss(t("q_next_online"), t("q_next_target"), t("q_cur"), ac, rw, dn,
+                                                          gamma, use_double)
+            assert np.array_equal(target.cpu().numpy(), d[f"target_{tag}"])
+            assert np.array_equal(q_sa.cpu().numpy(), d[f"q_sa_{tag}"])
+            ref = float(d[f"loss_{tag}"])
+            assert abs(loss.item() - ref) <= 1e-9 * abs(ref)
+
+
 def test_ddqn_target_loss_is_reentrant_across_streams(cuda):
     """include/b2048.h promises re-entrancy: the kernel owns no global scratch (one cluster, partial sums
     through distributed shared memory), so many launches in flight on several streams all return the

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import b2048
 from b2048 import env
 from oracle import board_oracle as bo
 
@@ -75,6 +76,37 @@ def test_step_all4_matches_reference_boards(cuda, boards_g):
         assert np.array_equal(rew4[:, a].cpu().numpy()[ok], g["reward"][:, a][ok].astype(np.int32))
 
 
+def test_bench_stream_head_matches_reference(cuda, golden_dir):
+    """SURVEY 8(d) parity subset: the device generators produce the bench stream the goldens were made from,
+    and the streaming kernel (1 Mi boards, so the persistent shared-memory-table path runs) agrees with the
+    REFERENCE on its first 65536 boards: slide-only successor (spawn off through the override hook), reward,
+    legal mask, done."""
+    d = np.load(os.path.join(golden_dir, "bench_stream.npz"))
+    m, n = len(d["boards"]), 1 << 20
+    boards = env.random_boards(n, seed=2048, device=cuda)
+    actions = env.random_actions(n, seed=2050, device=cuda)
+    assert np.array_equal(u64(boards[:m]), d["boards"]) and np.array_equal(actions[:m].cpu().numpy(), d["actions"])
+    assert np.array_equal(u64(boards[:4096]), bo.stream_boards(4096, seed=2048))
+    base = 1 << 35                                          # generators honour the global index base
+    assert np.array_equal(u64(env.random_boards(4099, seed=9, index_base=base + 3, p_empty=0.5, max_exp=15, device=cuda)),
+                          bo.stream_boards(4099, seed=9, index_base=base + 3, p_empty=0.5, max_exp=15))
+    assert np.array_equal(env.random_actions(4099, seed=9, step_index=5, index_base=base + 3, device=cuda).cpu().numpy(),
+                          bo.stream_actions(4099, seed=9, step=5, index_base=base + 3))
+    skip = torch.full((n,), 0xFE, dtype=torch.uint8, device=cuda)
+    nxt, rew, flg = env.step(boards, actions, spawn_override=skip)
+    f = flg[:m].cpu().numpy()
+    assert np.array_equal(u64(nxt[:m]), d["slide"]) and np.array_equal(rew[:m].cpu().numpy(), d["reward"])
+    assert np.array_equal(f & 0x0F, d["legal"]) and np.array_equal((f & 0x10) != 0, d["legal"] == 0)
+    # with spawns: identical to the slide-only board except for one new 2 / 4 in an empty cell, iff changed
+    nxt2, rew2, flg2 = env.step(boards, actions, seed=7, step_index=3)
+    assert torch.equal(rew2, rew) and torch.equal(flg2, flg)
+    x = (u64(nxt2[:m]) ^ d["slide"])
+    changed = (f & 0x20) != 0
+    assert np.array_equal(x != 0, changed)
+    nib = np.array([bin(int(v)).count("1") for v in x[changed][:2000]])
+    assert (nib == 1).all()
+
+
 def test_step_replays_reference_games(cuda, games_g):
     t = games_g
     S, A, R, S2, D = t["state"], t["action"], t["reward"], t["next"], t["done"]
@@ -94,7 +126,11 @@ def test_step_replays_reference_games(cuda, games_g):
 @pytest.mark.parametrize("n,index_base,offset", [
     (1, 0, 0), (2, 0, 0), (1000, 0, 0), (1001, 7, 0), (4097, 0, 1),        # small / unaligned kernel
     (1 << 20, 0, 0), ((1 << 20) + 1, 0, 0), (1 << 20, 12345, 0),            # streaming kernel (+tail, odd base)
-    (1 << 20, 1 << 33, 1),                                                  # misaligned view -> small kernel
+    ((1 << 20) + 7, 8, 0), ((1 << 19) + 8, 1 << 40, 0),                     # 7-board tail, one spare octet, huge base
+    (1 << 20, 1, 0), (1 << 20, 2, 0), (1 << 20, 3, 0), (1 << 20, 4, 0),     # every misalignment of the index base
+    (1 << 20, 5, 0), (1 << 20, 6, 0), (1 << 20, 7, 0),                      #   against the 8-board Philox groups
+    (1 << 20, 1 << 33, 1), (1 << 20, 0, 2),                                 # misaligned views -> small kernel
+    (1 << 20, 0, 4),                                                        # 32-byte aligned view -> streaming kernel
 ])
 def test_step_matches_oracle_with_philox_spawns(cuda, n, index_base, offset):
     """No override: the library's Philox spawn stream is reproduced by the oracle bit for bit, for
@@ -127,6 +163,73 @@ def test_step_fifty_percent_fours_and_high_tiles(cuda, index_base, max_exp):
     assert (max_exp < 15) == bool(ok.all())     # 32768+32768 merges exist (max_exp 15) and are flagged
     assert np.array_equal(u64(nxt)[ok], o_nxt[ok])
     assert np.array_equal(rew.cpu().numpy()[ok], o_rew[ok])
+
+
+def test_spawn_draws_are_uniform_and_value_is_independent_of_the_cell(cuda):
+    """Spawn stream v2 gives each board ONE 16-bit Philox lane d: rank = floor(d*n/65536), "4" iff the
+    fraction of d*n falls below p4.  Check on 16 Mi boards that, for every number of empty cells n, all
+    ranks are equally likely and the share of fours does not depend on the rank (5-sigma bands)."""
+    n = 1 << 24
+    boards = env.random_boards(n, seed=99, p_empty=0.5, max_exp=6, device=cuda)
+    actions = env.random_actions(n, seed=98, device=cuda)
+    skip = torch.full((n,), 0xFE, dtype=torch.uint8, device=cuda)
+    slid, _, flg = env.step(boards, actions, spawn_override=skip)
+    nxt, _, _ = env.step(boards, actions, seed=1234, step_index=7)
+    changed = (flg & 0x20) != 0
+    sh = 4 * torch.arange(16, device=cuda, dtype=torch.int64)
+    es = ((slid[:, None] >> sh) & 0xF)[changed]
+    en = ((nxt[:, None] >> sh) & 0xF)[changed]
+    diff = es != en
+    assert bool((diff.sum(dim=1) == 1).all())                       # exactly one new tile
+    cell = diff.to(torch.int64).argmax(dim=1)
+    val = en.gather(1, cell[:, None])[:, 0]
+    assert bool(((val == 1) | (val == 2)).all()) and bool((es.gather(1, cell[:, None]) == 0).all())
+    empty = es == 0
+    n_empty = empty.sum(dim=1)
+    rank = (empty.cumsum(dim=1) - 1).gather(1, cell[:, None])[:, 0]
+    for ne in range(1, 15):
+        m = n_empty == ne
+        tot = int(m.sum())
+        if tot < 20000:
+            continue
+        cnt = torch.bincount(rank[m], minlength=ne).double()
+        p = 1.0 / ne
+        sigma = (tot * p * (1 - p)) ** 0.5
+        assert float((cnt - tot * p).abs().max()) <= 5 * sigma + 1, (ne, cnt.tolist())
+        fours = torch.bincount(rank[m], weights=(val[m] == 2).double(), minlength=ne)
+        for r in range(ne):
+            c = float(cnt[r])
+            assert abs(float(fours[r]) - 0.1 * c) <= 5 * (c * 0.09) ** 0.5 + 1, (ne, r, float(fours[r]), c)
+
+
+def test_stream_kernel_split_launches(cuda):
+    """launch_step cuts a batch into launches of at most STREAM_MAX_OCTS octets (2^33 boards in the
+    shipped library: unreachable in a test).  build.py also builds a copy of the library with the limit
+    lowered to 40 000 octets; the 1 Mi-board call below is then 4 streaming launches with different
+    pointer / index-base offsets, and must still agree with the oracle bit for bit."""
+    import subprocess, sys, textwrap
+    lib = os.path.join(os.path.dirname(b2048._lib.LIB_PATH), "libb2048_splittest.so")
+    if not os.path.exists(lib):
+        pytest.fail(f"{lib} missing: run __graft_entry__.build()")
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path[:0] = [%r, %r]
+        from b2048 import env
+        from oracle import board_oracle as bo
+        dev = torch.device("cuda:0")
+        n = (1 << 20) + 13
+        for base in (0, 5):
+            b = env.random_boards(n, seed=31, device=dev); a = env.random_actions(n, seed=32, device=dev)
+            nxt, rew, flg = env.step(b, a, seed=77, step_index=3, index_base=base)
+            o = bo.step_packed(b.cpu().numpy().view(np.uint64), a.cpu().numpy(), seed=77, step=3, index_base=base,
+                               threads=bo.num_threads())
+            assert np.array_equal(nxt.cpu().numpy().view(np.uint64), o[0]) and np.array_equal(rew.cpu().numpy(), o[1])
+            assert np.array_equal(flg.cpu().numpy(), o[2])
+        print("SPLIT-OK")
+    """) % (os.path.dirname(os.path.dirname(b2048._lib.LIB_PATH)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2048_LIB=lib), capture_output=True, text=True,
+                       timeout=600)
+    assert "SPLIT-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_sharding_is_invisible(cuda):

@@ -28,7 +28,7 @@ REF_LEGAL_BOARDS = [
 @pytest.fixture(scope="module")
 def g(golden_dir):
     return {k: np.load(os.path.join(golden_dir, k + ".npz")) for k in
-            ("rows", "boards", "games", "dqn_conv", "dqn_dense", "egreedy")}
+            ("rows", "boards", "games", "dqn_conv", "dqn_dense", "egreedy", "dqn_dense_b5000", "bench_stream")}
 
 
 def test_reference_row_vectors():
@@ -162,6 +162,44 @@ def test_ddqn_target_loss_matches_reference(g, name, tag):
         else d["q_next_target"].max(1))
     t = d[f"target_{tag}"]
     assert (np.abs(g64 - t) > 1e-9 * np.abs(t)).any()
+
+
+def test_ddqn_oracle_on_config3_batch_5000_gamma_095_and_080(g):
+    """BASELINE.json config 3 as stated (dense Q-net, batch 5000, gamma 0.95; and the config module's 0.80):
+    the reference rounds gamma to float32, and 0.95 rounds differently from 0.80, so each value has its own
+    recorded targets.  Targets bit-identical, loss within 1e-12."""
+    d = g["dqn_dense_b5000"]
+    assert d["states"].shape == (5000, 16) and d["actions"].shape == (5000,)
+    st, ac, rw, ns, dn = do.extract_samples(bo.exponents(bo.pack(d["buf_state"])), d["buf_action"], d["buf_reward"],
+                                            bo.exponents(bo.pack(d["buf_next"])), d["buf_done"], d["idx"])
+    assert np.array_equal(st, d["states"]) and np.array_equal(ns, d["next_states"]) and np.array_equal(rw, d["rewards"])
+    for gamma, gtag in ((0.95, "g095"), (0.80, "g080")):
+        for use_double in (True, False):
+            tag = f"{gtag}_{'double' if use_double else 'single'}"
+            target, q_sa, loss, _ = do.ddqn_target_loss(d["q_next_online"], d["q_next_target"], d["q_cur"], d["actions"],
+                                                        d["rewards"], d["dones"], gamma, use_double)
+            assert np.array_equal(target, d[f"target_{tag}"]) and np.array_equal(q_sa, d[f"q_sa_{tag}"])
+            assert abs(loss - float(d[f"loss_{tag}"])) <= 1e-12 * abs(float(d[f"loss_{tag}"]))
+    # float32 rounding of gamma is visible: a float64 gamma would give different targets for 0.95
+    live = d["dones"] == 0
+    wrong = d["rewards"] + 0.95 * d["q_next_target"].max(axis=1)
+    assert not np.array_equal(wrong[live], d["target_g095_single"][live])
+
+
+def test_bench_stream_head_matches_reference(g):
+    """the first 65536 boards / actions of the BENCH stream (restated generators, seeds 2048 /
+    2050) went through the reference's Board2048 (oracle/gen_golden.py gen_bench_stream).  The oracle must
+    reproduce the inputs bit for bit and agree with the reference on slide-only successor, reward, legal mask."""
+    d = g["bench_stream"]
+    n = len(d["boards"])
+    assert n == 65536
+    assert np.array_equal(bo.stream_boards(n, seed=2048), d["boards"])
+    assert np.array_equal(bo.stream_actions(n, seed=2050, step=0), d["actions"])
+    skip = np.full(n, 0xFE, dtype=np.uint8)
+    nxt, rew, flg = bo.step_packed(d["boards"], d["actions"], spawn_override=skip)
+    assert np.array_equal(nxt, d["slide"]) and np.array_equal(rew, d["reward"])
+    assert np.array_equal(flg & 0x0F, d["legal"]) and np.array_equal((flg & 0x10) != 0, d["legal"] == 0)
+    assert np.array_equal(bo.legal_mask_packed(d["boards"]) & 0x0F, d["legal"])
 
 
 def test_conv_q_forward_matches_reference_q_values(g):

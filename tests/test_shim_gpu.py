@@ -265,6 +265,67 @@ def test_training_loop_runs_like_the_drivers_call_it(shim, kind, capsys):
     assert exp2.saves == 1
 
 
+def _astar_like_buffer(shim, n=300, maxlen=1000):
+    """A deque shaped like generate_replay_buffer_using_A_star's (src/state_space_search.py:104-131): real
+    Board2048 objects, the SAME board object as state and next state (:128), rewards computed child-minus-
+    parent style (so some are negative), `done` as an int."""
+    from collections import deque
+    rng = np.random.default_rng(7)
+    dq = deque(maxlen=maxlen)
+    b = shim.board.Board2048()
+    for i in range(n):
+        nb = b.peek_action(int(rng.integers(4)))
+        if not nb.available_moves():
+            nb = shim.board.Board2048()
+        reward = int(b.merge_score()) - int(nb.merge_score())          # <= 0, like reward(current, parent)
+        dq.append((nb, int(rng.integers(4)), reward, nb, int(i % 50 == 0)))
+        b = nb
+    return dq
+
+
+def test_replay_buffer_override_is_ingested_like_the_plain_deque(shim, monkeypatch, capsys):
+    """SURVEY 8(f) rank 3 / src/dqn_lib.py:169-170: training_loop(..., replay_buffer_override=deque) takes an
+    A*-seeded deque of (Board2048, action, reward, Board2048, done) tuples.  The GPU ring built from it
+    samples exactly the tensors the plain deque gives through the same numpy draw, keeps deque(maxlen)
+    semantics while the loop appends to it, and feeds train_step."""
+    from collections import deque
+    dq = _astar_like_buffer(shim)
+    assert any(e[2] < 0 for e in dq) and all(e[0] is e[3] for e in dq)
+    ring = shim.dqn._make_replay_buffer(15000, dq, True, "cuda:0")
+    assert isinstance(ring, shim.dqn.ReplayDeque) and len(ring) == len(dq) and ring.maxlen == dq.maxlen
+    for conv in (True, False):
+        to_tensor = shim.dqn.board_as_4d_tensor if conv else shim.dqn.board_as_flattened_tensor
+        extract = shim.dqn.extract_samples_conv if conv else shim.dqn.extract_samples_dense
+        np.random.seed(5)
+        got = shim.dqn.sample_experiences(512, ring, "cuda:0", to_tensor, extract)
+        np.random.seed(5)
+        want = shim.dqn.sample_experiences(512, deque(dq, maxlen=dq.maxlen), "cuda:0", to_tensor, extract)
+        for g, w in zip(got, want):
+            assert g.dtype == w.dtype and g.shape == w.shape and torch.equal(g, w)
+        assert torch.equal(got[0], got[3]) and bool((got[2] < 0).any())       # same board twice, negative rewards kept
+    # the whole loop with the override: the ring is what train_step sees, it grows by the played moves
+    seen = []
+    real_train_step = shim.dqn.train_step
+
+    def spy(batch_size, discount_factor, model, target_model, replay_buffer, *a, **kw):
+        seen.append((type(replay_buffer).__name__, len(replay_buffer)))
+        return real_train_step(batch_size, discount_factor, model, target_model, replay_buffer, *a, **kw)
+    monkeypatch.setattr(shim.dqn, "train_step", spy)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = conv_model().cuda()
+    exp = FakeExperiment()
+    shim.dqn.training_loop(15000, 3, 2, 0, 0.01, model, shim.dqn.reward_func_merge_score, shim.dqn.board_as_4d_tensor,
+                           "cuda:0", exp, 2, 0, 128, 0.8, copy.deepcopy(model), torch.nn.MSELoss(reduction="sum"),
+                           torch.optim.Adam(model.parameters(), lr=1e-2), True, 2, shim.dqn.extract_samples_conv,
+                           replay_buffer_override=dq)
+    capsys.readouterr()
+    assert [s[0] for s in seen] == ["ReplayDeque", "ReplayDeque"]               # episodes 1 and 2 train
+    # the ingested transitions are still there and every played step appended one more (up to maxlen)
+    assert len(dq) + 2 <= seen[0][1] <= dq.maxlen and seen[0][1] <= seen[1][1] <= dq.maxlen
+    assert seen[1][1] > seen[0][1] or seen[1][1] == dq.maxlen
+
+
 def test_one_hot_and_helpers(shim):
     t = torch.tensor([0, 3, 1], device="cuda")
     oh = shim.dqn.one_hot(t, 4, "cuda:0")
