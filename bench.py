@@ -252,12 +252,20 @@ def secondary_metrics(args, dev, rank, world, barrier):
     b2 = env.random_boards(n2, seed=SEED_BOARDS, index_base=rank * n2, device=dev)
     o2 = (torch.empty((n2, 4), dtype=torch.int64, device=dev), torch.empty((n2, 4), dtype=torch.int32, device=dev),
           torch.empty(n2, dtype=torch.uint8, device=dev))
-    for w in range(3):
-        env.step_all4(b2, seed=SEED_SPAWN, step_index=w, index_base=rank * n2, out=o2)
-    ms = timed(lambda i: env.step_all4(b2, seed=SEED_SPAWN, step_index=3 + i, index_base=rank * n2, out=o2), 50)
+    def all4_ms():
+        for w in range(3):
+            env.step_all4(b2, seed=SEED_SPAWN, step_index=w, index_base=rank * n2, out=o2)
+        return timed(lambda i: env.step_all4(b2, seed=SEED_SPAWN, step_index=3 + i, index_base=rank * n2, out=o2), 50)
+    ms = all4_ms()                                       # persistent kernel, row table staged in shared memory
+    os.environ["B2048_ALL4_FROM_L2"] = "1"               # A/B: one board per thread, row table gathered from L2
+    ms_l2 = all4_ms()
+    os.environ.pop("B2048_ALL4_FROM_L2", None)
     out["config2_all4"] = {"workload": "1Mi random boards x 4 actions per GPU (57 MB/launch: L2-resident, not a roofline run)",
                            "board_actions_per_sec": world * 4 * n2 / (ms * 1e-3), "ms_per_launch": ms,
-                           "algorithmic_GBps": n2 * 57 / (ms * 1e-3) / 1e9}
+                           "algorithmic_GBps": n2 * 57 / (ms * 1e-3) / 1e9,
+                           "kernel": "step_all4_stream_kernel (row table in shared memory, 8 boards per thread and Philox call)",
+                           "ab_table_from_l2": {"kernel": "step_all4_kernel (16 L2 gathers per board)", "ms_per_launch": ms_l2,
+                                                "board_actions_per_sec": world * 4 * n2 / (ms_l2 * 1e-3)}}
 
     # rollout: random policy incl. legal mask, replay append and masked reset (5 launches + torch bookkeeping / step)
     nv = 1 << 22
@@ -434,16 +442,19 @@ def run_ours(args):
     for w in range(args.warmup):
         env.step(boards, actions, seed=SEED_SPAWN, step_index=w, index_base=base, out=out)
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # Two events around the K back-to-back launches (none in between: the kernel uses programmatic dependent
+    # launch, and an event record between two launches would serialise them); one launch per step, so the
+    # kernel's average launch duration over the timed region is total / K.
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    ev[0].record()
+    ev0.record()
     for k in range(args.steps):
         env.step(boards, actions, seed=SEED_SPAWN, step_index=args.warmup + k, index_base=base, out=out)
-        ev[k + 1].record()
+    ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev0.elapsed_time(ev1)
+    kernel_ms = [total_ms / args.steps]
     clocks = None
     if rank == 0:
         clocks = sampler.summary(t_wall0, t_wall1)

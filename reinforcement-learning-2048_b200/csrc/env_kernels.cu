@@ -10,6 +10,8 @@
 // four boards per thread per iteration through 128-bit loads / stores, one Philox4x32-10 call
 // per four boards.  Small batches use `step_small_kernel`, which reads the L2-resident table
 // directly and so skips the 224 KB staging.
+#include <stdlib.h>
+
 #include "b2048_common.cuh"
 
 namespace b2048 {
@@ -121,6 +123,41 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+
+// Prologue of the persistent kernels: small per-action tables + run-time constants, then the row table
+// (bank-swizzled image, 224 KB) by seven 32 KB bulk copies that complete on `bar`.
+__device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* bar, const uint32_t* __restrict__ glut,
+                                             uint32_t p4) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 4) {
+    const ActXform x = act_xform((int)threadIdx.x);
+    uint32_t* row = reinterpret_cast<uint32_t*>(smem_raw + SM_ACT + 32 * threadIdx.x);
+    row[0] = x.sel_fwd & 0xFFFFu; row[1] = x.sel_fwd_hi; row[2] = x.sel_inv & 0xFFFFu; row[3] = x.sel_inv_hi;
+    row[4] = x.mul_l; row[5] = x.shift; row[6] = x.mask; row[7] = 0;
+  }
+  if (threadIdx.x == 0) {
+    uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
+    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4;
+  }
+  if (threadIdx.x < 128) {
+    const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
+    smem_raw[SM_LEGAL + threadIdx.x] =
+        (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
+                  ((m & 16u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
+    constexpr uint32_t CHUNK = 32768;  // 7 bulk copies of 32 KB
+#pragma unroll
+    for (uint32_t off = 0; off < (uint32_t)LUT_SMEM_BYTES; off += CHUNK)
+      bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut + LUT_ROWS) + off, CHUNK, bar);
+  }
+
 }
 
 // One board of the streaming kernel.  `sa` = shared base + 32 * action (row of both small tables).
@@ -302,34 +339,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   uint32_t sbase;   // shared-space base address, made opaque so that it lives in one register
   asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem_raw)));
 
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (threadIdx.x < 4) {
-    const ActXform x = act_xform((int)threadIdx.x);
-    uint32_t* row = reinterpret_cast<uint32_t*>(smem_raw + SM_ACT + 32 * threadIdx.x);
-    row[0] = x.sel_fwd & 0xFFFFu; row[1] = x.sel_fwd_hi; row[2] = x.sel_inv & 0xFFFFu; row[3] = x.sel_inv_hi;
-    row[4] = x.mul_l; row[5] = x.shift; row[6] = x.mask; row[7] = 0;
-  }
-  if (threadIdx.x == 0) {
-    uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
-    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4;
-  }
-  if (threadIdx.x < 128) {
-    const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
-    smem_raw[SM_LEGAL + threadIdx.x] =
-        (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
-                  ((m & 16u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
-    constexpr uint32_t CHUNK = 32768;  // 7 bulk copies of 32 KB
-#pragma unroll
-    for (uint32_t off = 0; off < (uint32_t)LUT_SMEM_BYTES; off += CHUNK)
-      bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut + LUT_ROWS) + off, CHUNK, bar);
-  }
+  // Programmatic dependent launch: the next kernel of the stream may start filling SMs as soon as this grid's
+  // CTAs retire (its 224 KB table staging then overlaps this grid's tail); everything that depends on the
+  // previous kernel's output waits at griddepcontrol.wait below.
+  asm volatile("griddepcontrol.launch_dependents;");
+
+  stage_tables(smem_raw, bar, glut, p4);
 
   // 32-bit octet / quad indices (the host wrapper keeps nocts < 2^31): every global address is then one
   // IMAD.WIDE (base + index * size) on the FMA pipe instead of 64-bit LEA pairs on the ALU pipe.
@@ -340,6 +355,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   const uint64_t pidx_base = index_base >> 3;
   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32);
 
+  // boards / actions may come from the previous kernel in the stream (rollouts step next -> boards): wait for
+  // it to complete and flush; the table staging above does not depend on it
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // the first loads are issued before waiting for the table
   uint4 xa = make_uint4(0, 0, 0, 0), xb = xa, ya = xa, yb = xa;
   uint32_t ax = 0, ay = 0, ox = 0xFFFFFFFFu, oy = 0xFFFFFFFFu;
@@ -458,6 +476,134 @@ __global__ void __launch_bounds__(256)
   st_stream_v8(next4 + 2 * i, make_uint4(nl[0], nh[0], nl[1], nh[1]), make_uint4(nl[2], nh[2], nl[3], nh[3]));
   st_stream_v4(reward4 + i, make_uint4(rw[0], rw[1], rw[2], rw[3]));
   flags[i] = (uint8_t)f;
+}
+
+// ---- all four actions, persistent variant: row table in shared memory ---------------------------------------
+// BASELINE.json config 2 at >= 512 Ki boards.  One thread owns EIGHT consecutive boards (one Philox call, two
+// 256-bit loads) and walks them in a rolled loop; per board the four moves are unrolled with their transform
+// constants folded into immediates (the action is a compile-time constant here, unlike in K1), the 16 row
+// lookups go to the staged table, and the three stores are full-sector (32 B next4, 16 B reward4, 1 B flags).
+// A board whose lookups were clamped (or that really overflows) is redone from the global table.
+// CTA size: 512 threads (96 registers) run the loop fastest (77 us per 4 Mi boards against 97 us with 896);
+// 896 threads (72 registers) are used when they let every thread finish in ONE pass (1 Mi boards: 22.8 vs 24.8 us).
+constexpr int ALL4_THREADS = 512, ALL4_THREADS_WIDE = 896;
+
+template <int A>
+__device__ __forceinline__ void slide_fixed(uint32_t sbase, const StreamConsts& kc, uint32_t lo, uint32_t hi,
+                                            uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& changed,
+                                            uint32_t& fl) {
+  constexpr ActXform x = act_xform(A);
+  uint32_t zl = lo, zh = hi;
+  if (A != 2) {                                   // left: identity
+    zl = __byte_perm(lo, hi, x.sel_fwd & 0xFFFFu);
+    zh = __byte_perm(lo, hi, x.sel_fwd_hi);
+    zl = delta_swap(zl, x);
+    zh = delta_swap(zh, x);
+  }
+  const uint32_t cl = __vminu2(zl, LUT_LIM2), ch = __vminu2(zh, LUT_LIM2);
+  const uint32_t sl = cl ^ ((cl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+  const uint32_t sh = ch ^ ((ch >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+  const uint32_t e0 = lds32(__dp2a_lo(sl, K_W4(kc), sbase));
+  const uint32_t e1 = lds32(__dp2a_hi(sl, K_W4(kc), sbase));
+  const uint32_t e2 = lds32(__dp2a_lo(sh, K_W4(kc), sbase));
+  const uint32_t e3 = lds32(__dp2a_hi(sh, K_W4(kc), sbase));
+  uint32_t wl = __byte_perm(e0, e1, 0x5410);
+  uint32_t wh = __byte_perm(e2, e3, 0x5410);
+  const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
+  const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
+  fl |= h01 | h23;
+  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));
+  changed = (wl ^ zl) | (wh ^ zh);
+  if (A != 2) {
+    wl = delta_swap(wl, x);
+    wh = delta_swap(wh, x);
+    olo = __byte_perm(wl, wh, x.sel_inv & 0xFFFFu);
+    ohi = __byte_perm(wl, wh, x.sel_inv_hi);
+  } else {
+    olo = wl;
+    ohi = wh;
+  }
+}
+
+template <bool HAS_OVERRIDE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    step_all4_stream_kernel(const uint4* __restrict__ boards2, uint4* __restrict__ next4,
+                            uint4* __restrict__ reward4, uint8_t* __restrict__ flags, int64_t nocts,
+                            const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
+                            uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SM_BAR);
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem_raw)));
+  stage_tables(smem_raw, bar, glut, p4);
+  const uint32_t stride = gridDim.x * THREADS;
+  const uint32_t no = (uint32_t)nocts;
+  uint32_t oct = blockIdx.x * THREADS + threadIdx.x;
+  const uint64_t pidx_base = index_base >> 3;          // the host wrapper only sends index bases that are multiples of 8
+  uint4 b[4];
+  if (oct < no) {
+    ld_stream_v8(boards2 + 4u * oct, b[0], b[1]);
+    ld_stream_v8(boards2 + 4u * oct + 2, b[2], b[3]);
+  }
+  mbar_wait(bar, 0);
+  StreamConsts kc;
+  {
+    const uint4 k = lds128(sbase + SM_CONST);
+    kc.one = k.y; kc.k4 = k.x; kc.k16 = k.z; kc.k44 = k.w;
+    kc.p4 = lds32(sbase + SM_CONST + 16);
+  }
+  const Add7Fma add{kc.one};
+  while (oct < no) {
+    const uint64_t pidx = pidx_base + oct;
+    const uint4 w = philox4x32_10<SPAWN_PHILOX_ROUNDS>(
+        make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), (uint32_t)step, (uint32_t)(step >> 32)), keys);
+    const uint32_t words[8] = {b[0].x, b[0].y, b[0].z, b[0].w, b[1].x, b[1].y, b[1].z, b[1].w};
+    const uint32_t words2[8] = {b[2].x, b[2].y, b[2].z, b[2].w, b[3].x, b[3].y, b[3].z, b[3].w};
+#pragma unroll 1
+    for (uint32_t j = 0; j < 8; ++j) {
+      // board j of the octet: registers are picked with predicated moves (a rolled loop keeps the code small)
+      uint32_t lo, hi;
+      {
+        const uint32_t jj = j & 3u;
+        const uint32_t l0 = j < 4 ? words[0] : words2[0], h0 = j < 4 ? words[1] : words2[1];
+        const uint32_t l1 = j < 4 ? words[2] : words2[2], h1 = j < 4 ? words[3] : words2[3];
+        const uint32_t l2 = j < 4 ? words[4] : words2[4], h2 = j < 4 ? words[5] : words2[5];
+        const uint32_t l3 = j < 4 ? words[6] : words2[6], h3 = j < 4 ? words[7] : words2[7];
+        lo = jj == 0 ? l0 : jj == 1 ? l1 : jj == 2 ? l2 : l3;
+        hi = jj == 0 ? h0 : jj == 1 ? h1 : jj == 2 ? h2 : h3;
+      }
+      const uint32_t D = draw_lane(w, j);
+      const uint32_t i = 8u * oct + j;
+      const uint32_t o4 = HAS_OVERRIDE ? override4[i] : 0xFFFFFFFFu;
+      uint32_t nl[4], nh[4], rw[4], ch[4], fl = 0, f = 0;
+      slide_fixed<0>(sbase, kc, lo, hi, nl[0], nh[0], rw[0], ch[0], fl);
+      slide_fixed<1>(sbase, kc, lo, hi, nl[1], nh[1], rw[1], ch[1], fl);
+      slide_fixed<2>(sbase, kc, lo, hi, nl[2], nh[2], rw[2], ch[2], fl);
+      slide_fixed<3>(sbase, kc, lo, hi, nl[3], nh[3], rw[3], ch[3], fl);
+      uint32_t legal = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        legal |= ch[a] ? (1u << a) : 0u;
+        finish_board<HAS_OVERRIDE>(nl[a], nh[a], ch[a], D, K_P4(kc, p4), HAS_OVERRIDE ? ((o4 >> (8 * a)) & 0xFFu) : 0xFFu,
+                                   f, add);
+      }
+      if (__builtin_expect((fl & 0x80008000u) != 0u, 0)) {      // clamped or overflowing row: redo from the global table
+        uint32_t f2;
+        all4_board<HAS_OVERRIDE>(lo, hi, nullptr, glut, D, p4, o4, nl, nh, rw, f2);
+        f = f2;
+      } else {
+        f = legal | (legal ? 0u : (uint32_t)B2048_FLAG_DONE) | (f & B2048_FLAG_BADSPAWN);
+      }
+      st_stream_v8(next4 + 2u * i, make_uint4(nl[0], nh[0], nl[1], nh[1]), make_uint4(nl[2], nh[2], nl[3], nh[3]));
+      st_stream_v4(reward4 + i, make_uint4(rw[0], rw[1], rw[2], rw[3]));
+      flags[i] = (uint8_t)f;
+    }
+    oct += stride;
+    if (oct < no) {
+      ld_stream_v8(boards2 + 4u * oct, b[0], b[1]);
+      ld_stream_v8(boards2 + 4u * oct + 2, b[2], b[3]);
+    }
+  }
 }
 
 // ---- helpers: legal mask, reset, pack/unpack, synthetic inputs ---------------------------------
@@ -659,12 +805,22 @@ cudaError_t launch_step(const DeviceCtx* ctx, const uint64_t* boards, const uint
     for (int64_t o0 = 0; o0 < nocts_total; o0 += STREAM_MAX_OCTS) {
       const int64_t nocts = (nocts_total - o0 < STREAM_MAX_OCTS) ? (nocts_total - o0) : STREAM_MAX_OCTS;
       const int64_t b0 = o0 * 8;
-      step_stream_kernel<HAS_OVERRIDE><<<ctx->sm_count, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(
-          reinterpret_cast<const uint4*>(boards + b0), reinterpret_cast<const uint32_t*>(actions + b0),
-          reinterpret_cast<uint4*>(next + b0), reinterpret_cast<uint4*>(reward + b0),
-          reinterpret_cast<uint32_t*>(flags + b0), nocts, ctx->lut, philox_keys(seed, DOM_SPAWN), step,
-          index_base + (uint64_t)b0, p4, ovr ? reinterpret_cast<const uint32_t*>(ovr + b0) : nullptr);
-      cudaError_t e = cudaGetLastError();
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)ctx->sm_count, 1, 1);
+      cfg.blockDim = dim3(STREAM_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = STREAM_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see griddepcontrol.* in the kernel
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(
+          &cfg, step_stream_kernel<HAS_OVERRIDE>, reinterpret_cast<const uint4*>(boards + b0),
+          reinterpret_cast<const uint32_t*>(actions + b0), reinterpret_cast<uint4*>(next + b0),
+          reinterpret_cast<uint4*>(reward + b0), reinterpret_cast<uint32_t*>(flags + b0), nocts,
+          (const uint32_t*)ctx->lut, philox_keys(seed, DOM_SPAWN), step, index_base + (uint64_t)b0, p4,
+          ovr ? reinterpret_cast<const uint32_t*>(ovr + b0) : (const uint32_t*)nullptr);
       if (e != cudaSuccess) return e;
     }
     done = nocts_total * 8;
@@ -686,7 +842,18 @@ cudaError_t env_kernels_configure() {
   cudaError_t e = cudaFuncSetAttribute(step_stream_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(step_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(step_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(step_all4_stream_kernel<false, ALL4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           STREAM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(step_all4_stream_kernel<true, ALL4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           STREAM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(step_all4_stream_kernel<false, ALL4_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           STREAM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(step_all4_stream_kernel<true, ALL4_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               STREAM_SMEM_BYTES);
 }
 
@@ -726,16 +893,42 @@ extern "C" int b2048_step_all4(const uint64_t* boards, uint64_t* next4, int32_t*
   if (reinterpret_cast<uintptr_t>(spawn_override4) & 3u) return B2048_EINVAL;
   B2048_CTX_OR_RETURN();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)blocks_for(n, 256);
-  if (spawn_override4)
-    step_all4_kernel<true><<<grid, 256, 0, st>>>(boards, reinterpret_cast<uint4*>(next4),
-                                                 reinterpret_cast<uint4*>(reward4), flags, n, ctx->lut,
-                                                 seed, step, index_base, p4_threshold,
-                                                 reinterpret_cast<const uint32_t*>(spawn_override4));
-  else
-    step_all4_kernel<false><<<grid, 256, 0, st>>>(boards, reinterpret_cast<uint4*>(next4),
-                                                  reinterpret_cast<uint4*>(reward4), flags, n, ctx->lut,
-                                                  seed, step, index_base, p4_threshold, nullptr);
+  int64_t done = 0;
+  const char* force_l2 = getenv("B2048_ALL4_FROM_L2");          // A/B switch (bench.py extra.config2_all4)
+  // persistent shared-memory-table kernel for large aligned batches; the rest (and everything small) reads the
+  // table from L2, one board per thread
+  if (n >= STREAM_MIN_BOARDS && (index_base & 7u) == 0 && (reinterpret_cast<uintptr_t>(boards) & 31u) == 0 &&
+      !(force_l2 && force_l2[0] == '1') && n / 8 < ((int64_t)1 << 28)) {
+    const int64_t nocts = n / 8;
+    const bool wide = nocts <= (int64_t)ctx->sm_count * ALL4_THREADS_WIDE;      // one pass with the wide CTA
+#define LAUNCH_ALL4(OVR, T)                                                                                          \
+  step_all4_stream_kernel<OVR, T><<<ctx->sm_count, T, STREAM_SMEM_BYTES, st>>>(                                      \
+      reinterpret_cast<const uint4*>(boards), reinterpret_cast<uint4*>(next4), reinterpret_cast<uint4*>(reward4), flags, \
+      nocts, ctx->lut, philox_keys(seed, DOM_SPAWN), step, index_base, p4_threshold,                                 \
+      reinterpret_cast<const uint32_t*>(spawn_override4))
+    if (spawn_override4) {
+      if (wide) LAUNCH_ALL4(true, ALL4_THREADS_WIDE); else LAUNCH_ALL4(true, ALL4_THREADS);
+    } else {
+      if (wide) LAUNCH_ALL4(false, ALL4_THREADS_WIDE); else LAUNCH_ALL4(false, ALL4_THREADS);
+    }
+#undef LAUNCH_ALL4
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    done = nocts * 8;
+  }
+  if (done < n) {
+    const int64_t m = n - done;
+    const unsigned grid = (unsigned)blocks_for(m, 256);
+    if (spawn_override4)
+      step_all4_kernel<true><<<grid, 256, 0, st>>>(boards + done, reinterpret_cast<uint4*>(next4 + 4 * done),
+                                                   reinterpret_cast<uint4*>(reward4 + 4 * done), flags + done, m, ctx->lut,
+                                                   seed, step, index_base + (uint64_t)done, p4_threshold,
+                                                   reinterpret_cast<const uint32_t*>(spawn_override4 + 4 * done));
+    else
+      step_all4_kernel<false><<<grid, 256, 0, st>>>(boards + done, reinterpret_cast<uint4*>(next4 + 4 * done),
+                                                    reinterpret_cast<uint4*>(reward4 + 4 * done), flags + done, m, ctx->lut,
+                                                    seed, step, index_base + (uint64_t)done, p4_threshold, nullptr);
+  }
   return (int)cudaGetLastError();
 }
 

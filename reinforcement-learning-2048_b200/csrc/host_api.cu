@@ -245,7 +245,9 @@ extern "C" int b2048_host_alloc(void** out, size_t bytes, int device, int* numa_
   cpu_set_t prev, want;
   int node = -1;
   const bool have_prev = sched_getaffinity(0, sizeof(prev), &prev) == 0;
-  const bool bind = have_prev && local_cpus(device, &want, &node) && sched_setaffinity(0, sizeof(want), &want) == 0;
+  const char* off = getenv("B2048_NO_NUMA_BIND");          // A/B switch for profiles/pinned_ab.py
+  const bool bind = !(off && off[0] == '1') && have_prev && local_cpus(device, &want, &node) &&
+                    sched_setaffinity(0, sizeof(want), &want) == 0;
   int prev_dev = 0;
   cudaGetDevice(&prev_dev);
   cudaSetDevice(device);

@@ -248,15 +248,30 @@ def test_sharding_is_invisible(cuda):
                 assert torch.equal(w[sl], p)
 
 
-def test_all4_consistent_with_step(cuda):
-    n = 1 << 16
-    boards = env.random_boards(n, seed=11, device=cuda)
-    nxt4, rew4, flg4 = env.step_all4(boards, seed=8, step_index=1)
+@pytest.mark.parametrize("n,max_exp,index_base", [(1 << 16, 11, 0), ((1 << 20) + 5, 11, 0), (1 << 20, 15, 8 << 30),
+                                                  (1 << 20, 11, 3)])
+def test_all4_consistent_with_step(cuda, n, max_exp, index_base):
+    """b2048_step_all4 (BASELINE config 2) == four b2048_step calls, for the one-board-per-thread kernel
+    (64 Ki boards; also index bases that are not multiples of 8) and for the persistent shared-memory-table
+    kernel (>= 512 Ki boards, incl. a ragged tail and boards with 16384 / 32768 tiles that take its cold path)."""
+    boards = env.random_boards(n, seed=11, max_exp=max_exp, device=cuda)
+    nxt4, rew4, flg4 = env.step_all4(boards, seed=8, step_index=1, index_base=index_base)
     for a in range(4):
-        nxt, rew, flg = env.step(boards, torch.full((n,), a, dtype=torch.uint8, device=cuda), seed=8, step_index=1)
-        assert torch.equal(nxt4[:, a], nxt) and torch.equal(rew4[:, a], rew)
+        nxt, rew, flg = env.step(boards, torch.full((n,), a, dtype=torch.uint8, device=cuda), seed=8, step_index=1,
+                                 index_base=index_base)
+        ok = (flg & 0x40) == 0                           # next / reward are unspecified for overflowing moves
+        assert torch.equal(nxt4[:, a][ok], nxt[ok]) and torch.equal(rew4[:, a][ok], rew[ok])
         assert torch.equal(flg4 & 0x1F, flg & 0x1F)
         assert torch.equal(((flg4 >> a) & 1).bool(), (flg & 0x20) != 0)   # legal == changed
+        assert bool(((flg4 & 0x40) >= (flg & 0x40)).all())                # an overflow in any direction is flagged
+    if max_exp < 15:
+        assert not bool((flg4 & 0x40).any())
+    # against the oracle too (all four successors of the first boards)
+    m = min(n, 4096)
+    for a in range(4):
+        o = bo.step_packed(u64(boards[:m]), np.full(m, a, dtype=np.uint8), seed=8, step=1, index_base=index_base)
+        ok = (o[2] & 0x40) == 0
+        assert np.array_equal(u64(nxt4[:m, a].contiguous())[ok], o[0][ok]) and np.array_equal(rew4[:m, a].cpu().numpy()[ok], o[1][ok])
 
 
 def test_legal_mask_reset_pack_unpack(cuda, boards_g):
