@@ -278,6 +278,25 @@ int p2p_allreduce_adam_f64(const double* const* peer_grads, uint64_t* const* pee
                            double* exp_avg, double* exp_avg_sq, int64_t* step_counter, int64_t n,
                            double lr, double beta1, double beta2, double eps, void* stream);
 
+/* ---- K8: float64 tensor-core layers of the dense Q-network (src/configs/double_dqn_dense.py:7-15) -------------- */
+
+/* nn.Linear forward, optionally fused with ReLU: c[rows, n_out] = act(a[rows, n_in] w[n_out, n_in]^T + bias[n_out]).
+ * Row-major float64, 16-byte aligned pointers, n_in even; n_out even, or n_out == 4 with relu == 0 (the Q-value
+ * layer).  Replaces model(states) / model(next_states) / target_model(next_states), src/dqn_lib.py:126-147. */
+int dense_linear_forward_f64(const double* a, const double* w, const double* bias, double* c, int64_t rows, int n_in,
+                             int n_out, int relu, void* stream);
+/* Input gradient of a Linear layer fused with the ReLU mask of the layer below:
+ * dz[rows, n_in] = (g[rows, n_out] w[n_out, n_in]) * (h[rows, n_in] > 0), h = that layer's (post-ReLU) output. */
+int dense_linear_dgrad_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows, int n_in,
+                           int n_out, void* stream);
+/* Weight and bias gradient: dw[n_out, n_in] = g^T x, db[n_out] = column sums of g over `rows` rows (x = the layer's
+ * input).  The rows are split over the SMs; per-split products go to `scratch`
+ * (dense_linear_wgrad_scratch_elems(rows, n_in, n_out) doubles, 16-byte aligned) and are added in a fixed order,
+ * so results are bit-reproducible.  Overwrites dw / db (no zeroing needed). */
+int64_t dense_linear_wgrad_scratch_elems(int64_t rows, int n_in, int n_out);
+int dense_linear_wgrad_f64(const double* g, const double* x, double* dw, double* db, double* scratch, int64_t rows,
+                           int n_in, int n_out, void* stream);
+
 /* ---- K0: batched epsilon-greedy ---------------------------------------------------------------- */
 
 /* = epsilon_greedy_policy, src/dqn_lib.py:16-30, for n boards.  With probability eps the action is

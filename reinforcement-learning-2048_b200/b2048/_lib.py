@@ -64,6 +64,10 @@ SIGNATURES = {
     "p2p_allreduce_adam_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_double, c_void_p]),
+    "dense_linear_forward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "dense_linear_dgrad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dense_linear_wgrad_scratch_elems": (c_int64, [c_int64, c_int, c_int]),
+    "dense_linear_wgrad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "egreedy_select": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_uint64, c_uint64, c_uint64,
                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "layer_wgrad_small_scratch_elems": (c_int64, [c_int64, c_int, c_int]),

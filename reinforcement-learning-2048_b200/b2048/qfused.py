@@ -226,7 +226,10 @@ class TrainableConvQ(nn.Module):
 
 
 def accelerate_inference(net: nn.Module):
-    """The fastest no-gradient evaluator for `net`: the fused kernel for the reference's conv
-    Q-network, otherwise `qnet.accelerate(net)` (float64 GEMM path)."""
+    """The fastest no-gradient evaluator for `net`: the fused kernel K6 for the reference's conv
+    Q-network, the tensor-core layers K8 for its dense one, otherwise `qnet.accelerate(net)`."""
+    from . import qdense
     from .qnet import accelerate
-    return FusedConvQ(net) if matches(net) else accelerate(net)
+    if matches(net):
+        return FusedConvQ(net)
+    return qdense.DenseQ(net) if qdense.matches(net) else accelerate(net)

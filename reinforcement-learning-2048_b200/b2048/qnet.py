@@ -157,9 +157,12 @@ class FastQNet(nn.Module):
 
 def accelerate(net: nn.Module) -> nn.Module:
     """The fastest evaluator with gradients for `net`: `qfused.TrainableConvQ` (K6 forward, K7 backward)
-    for the reference's conv Q-network, FastQNet for other float64 CUDA Sequentials of plain small
+    for the reference's conv Q-network, `qdense.TrainableDenseQ` (K8) for its dense one and other
+    Linear / ReLU stacks with four outputs, FastQNet for other float64 CUDA Sequentials of plain small
     convolutions + ReLU / Flatten / Linear, otherwise the module itself."""
-    from . import qfused
+    from . import qdense, qfused
     if qfused.matches(net):
         return qfused.TrainableConvQ(net)
+    if qdense.matches(net):
+        return qdense.TrainableDenseQ(net)
     return FastQNet(net) if FastQNet.supports(net) else net

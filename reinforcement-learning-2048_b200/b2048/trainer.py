@@ -14,6 +14,7 @@ import copy
 import torch
 
 from . import ddqn, dist as bdist
+from .qdense import DenseQ
 from .qfused import FusedConvQ, TrainableConvQ, accelerate_inference
 from .qnet import accelerate
 from .replay import ReplayRing
@@ -62,7 +63,7 @@ class DDQNUpdater:
         return x.view(self.B, 1, 4, 4) if self.conv else x
 
     def _infer(self, net, x):
-        return net(x) if isinstance(net, FusedConvQ) else net(self._shape(x))
+        return net(x) if isinstance(net, (FusedConvQ, DenseQ)) else net(self._shape(x))
 
     def _update_eager(self):
         states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
@@ -78,7 +79,7 @@ class DDQNUpdater:
             self.side2.wait_stream(main)
             with torch.cuda.stream(self.side2), torch.no_grad():
                 q_next_online = self._infer(self.i_model, next_states)
-        direct = isinstance(self.f_model, TrainableConvQ)      # conv config: no autograd graph at all
+        direct = hasattr(self.f_model, "forward_saving")       # conv (K6/K7) and dense (K8) configs: no autograd graph at all
         if direct:
             q_cur, saved = self.f_model.forward_saving(states)
         else:

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b2048", "libb2048.so")
-SOURCES = ["env_kernels.cu", "replay_kernels.cu", "ddqn_kernels.cu", "p2p_kernels.cu", "qnet_kernels.cu", "wgrad_kernels.cu", "host_api.cu"]
+SOURCES = ["env_kernels.cu", "replay_kernels.cu", "ddqn_kernels.cu", "p2p_kernels.cu", "qnet_kernels.cu", "wgrad_kernels.cu", "dense_kernels.cu", "host_api.cu"]
 HEADERS = ["b2048_common.cuh", os.path.join("..", "..", "include", "b2048.h")]
 
 

@@ -133,6 +133,74 @@ def test_updater_graph_equals_eager_and_learns(cuda):
     assert all(torch.equal(p, q) for p, q in zip(c.model.parameters(), c.target.parameters()))
 
 
+@pytest.mark.parametrize("rows,n_in,n_out", [(5000, 512, 512), (5000, 512, 256), (5000, 16, 512), (5000, 256, 4),
+                                             (1, 512, 256), (7, 16, 512), (137, 64, 128), (4097, 48, 64), (300, 130, 6)])
+def test_dense_tensor_core_layers_match_torch(cuda, rows, n_in, n_out):
+    """K8 (dense_kernels.cu): nn.Linear forward (+ReLU), input gradient (+ReLU mask) and weight / bias gradient on
+    the FP64 tensor cores against torch float64, element-wise 1e-9 relative (+1e-12 absolute: sums of O(100)
+    terms of mixed sign; measured agreement ~1e-14), incl. ragged row counts and widths that fill only part of a tile."""
+    from b2048 import _lib
+    from b2048.env import _ptr, _stream
+    g = torch.Generator(device="cpu").manual_seed(rows * 31 + n_in)
+    x = torch.randn(rows, n_in, dtype=torch.float64, generator=g).to(cuda)
+    w = (torch.randn(n_out, n_in, dtype=torch.float64, generator=g) * 0.1).to(cuda)
+    b = torch.randn(n_out, dtype=torch.float64, generator=g).to(cuda)
+    gy = torch.randn(rows, n_out, dtype=torch.float64, generator=g).to(cuda)
+    h = torch.randn(rows, n_in, dtype=torch.float64, generator=g).to(cuda)     # "output of the layer below" for the mask
+    L, st = _lib.lib(), _stream(x)
+
+    def close(got, want):
+        tol = 1e-9 * want.abs() + 1e-12 * max(1.0, float(want.abs().max()))
+        assert bool(((got - want).abs() <= tol).all()), float((got - want).abs().max())
+
+    for relu in ((0,) if n_out == 4 else (0, 1)):
+        out = torch.full((rows, n_out), float("nan"), dtype=torch.float64, device=cuda)
+        _lib.check(L.dense_linear_forward_f64(_ptr(x), _ptr(w), _ptr(b), _ptr(out), rows, n_in, n_out, relu, st))
+        want = torch.addmm(b, x, w.t())
+        close(out, torch.relu(want) if relu else want)
+    dz = torch.full((rows, n_in), float("nan"), dtype=torch.float64, device=cuda)
+    _lib.check(L.dense_linear_dgrad_f64(_ptr(gy), _ptr(w), _ptr(h), _ptr(dz), rows, n_in, n_out, st))
+    close(dz, (gy @ w) * (h > 0))
+    scratch = torch.empty(int(L.dense_linear_wgrad_scratch_elems(rows, n_in, n_out)), dtype=torch.float64, device=cuda)
+    dw = torch.full((n_out, n_in), float("nan"), dtype=torch.float64, device=cuda)
+    db = torch.full((n_out,), float("nan"), dtype=torch.float64, device=cuda)
+    _lib.check(L.dense_linear_wgrad_f64(_ptr(gy), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), rows, n_in, n_out, st))
+    close(dw, gy.t() @ x)
+    close(db, gy.sum(dim=0))
+    dw2, db2 = torch.empty_like(dw), torch.empty_like(db)                          # bit-reproducible
+    _lib.check(L.dense_linear_wgrad_f64(_ptr(gy), _ptr(x), _ptr(dw2), _ptr(db2), _ptr(scratch), rows, n_in, n_out, st))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("n", [1, 33, 5000])
+def test_dense_q_network_forward_and_backward_match_autograd(cuda, n):
+    """DenseQ / TrainableDenseQ on the reference's dense Q-network against the nn.Sequential itself."""
+    from b2048.qdense import DenseQ, TrainableDenseQ, matches
+    torch.manual_seed(n)
+    net = dense_model().to(cuda)
+    assert matches(net) and not matches(conv_model().to(cuda))
+    x = torch.randn(n, 16, dtype=torch.float64, device=cuda) * 3
+    want = net(x)
+    got = DenseQ(net)(x)
+    assert bool(((got - want).abs() <= 1e-9 * want.abs() + 1e-12).all())
+    tq = TrainableDenseQ(net)
+    gq = torch.randn(n, 4, dtype=torch.float64, device=cuda)
+    want.backward(gq)
+    ref = [p.grad.clone() for p in net.parameters()]
+    q, saved = tq.forward_saving(x)
+    assert torch.equal(q, got)
+    grads = [torch.full_like(p, float("nan")) for p in net.parameters()]
+    tq.backward_into(saved, gq, grads)
+    for a, b in zip(grads, ref):
+        assert bool(((a - b).abs() <= 1e-9 * b.abs() + 1e-12 * max(1.0, float(b.abs().max()))).all()), float((a - b).abs().max())
+    # the autograd entry point (dqn_lib.train_step with the caller's loss and optimizer)
+    for p in net.parameters():
+        p.grad = None
+    (tq(x) * gq).sum().backward()
+    for p, b in zip(net.parameters(), ref):
+        assert bool(((p.grad - b).abs() <= 1e-9 * b.abs() + 1e-12 * max(1.0, float(b.abs().max()))).all())
+
+
 def _other_conv_model():
     from torch import nn   # not the reference's widths: exercises the generic FastQNet path
     return nn.Sequential(nn.Conv2d(1, 32, kernel_size=2), nn.ReLU(), nn.Conv2d(32, 64, kernel_size=2), nn.ReLU(),
