@@ -157,7 +157,6 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
     for (uint32_t off = 0; off < (uint32_t)LUT_SMEM_BYTES; off += CHUNK)
       bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(glut + LUT_ROWS) + off, CHUNK, bar);
   }
-
 }
 
 // One board of the streaming kernel.  `sa` = shared base + 32 * action (row of both small tables).
