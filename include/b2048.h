@@ -286,7 +286,8 @@ int p2p_allreduce_adam_f64(const double* const* peer_grads, uint64_t* const* pee
 int dense_linear_forward_f64(const double* a, const double* w, const double* bias, double* c, int64_t rows, int n_in,
                              int n_out, int relu, void* stream);
 /* Input gradient of a Linear layer fused with the ReLU mask of the layer below:
- * dz[rows, n_in] = (g[rows, n_out] w[n_out, n_in]) * (h[rows, n_in] > 0), h = that layer's (post-ReLU) output. */
+ * dz[rows, n_in] = (g[rows, n_out] w[n_out, n_in]) * (h[rows, n_in] > 0), h = that layer's (post-ReLU) output;
+ * h == NULL gives the plain product (the conv Q-network's patch-matrix gradient, masked later). */
 int dense_linear_dgrad_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows, int n_in,
                            int n_out, void* stream);
 /* Weight and bias gradient: dw[n_out, n_in] = g^T x, db[n_out] = column sums of g over `rows` rows (x = the layer's

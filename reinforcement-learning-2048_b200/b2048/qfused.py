@@ -107,8 +107,8 @@ def conv_q_forward_saving(x, params):
 def conv_q_backward(saved, params, gq, out=None):
     """Gradients of the eight parameter tensors given gq = d loss / d q [n,4]: per layer the K7 weight /
     bias gradient kernels on the saved matrices (on a side stream: they are leaves of the dependency chain
-    g4 -> g3 -> g2 -> g1), cuBLAS DGEMMs for the input gradients, ATen's threshold_backward for the ReLU
-    masks and one fused kernel for the first convolution.  `out` (optional): eight contiguous tensors in parameter order that
+    g4 -> g3 -> g2 -> g1), the K8 tensor-core kernel for the input gradients (fused with the ReLU masks; round 1:
+    cuBLAS DGEMMs + ATen threshold_backward) and one fused kernel for the first convolution.  `out` (optional): eight contiguous tensors in parameter order that
     receive the gradients (overwritten, not accumulated) — e.g. the views of a flat gradient buffer."""
     x, p2, a2, a3 = saved
     w2, w3, w4 = params[2], params[4], params[6]
@@ -146,20 +146,23 @@ def conv_q_backward(saved, params, gq, out=None):
     # Per layer: the input-gradient GEMM (critical path) is launched first, the weight-gradient kernel of
     # the same layer second, on the side stream, waiting only for g: it fills in behind the GEMM's CTAs
     # instead of taking the SMs' shared memory ahead of it.
-    relu_grad = torch.ops.aten.threshold_backward
+    def dgrad(g, w2d, h, rows, n_in, n_out):    # (g w) * (h > 0) on the FP64 tensor cores (K8); h None: no mask
+        dz = torch.empty((rows, n_in), **kw)
+        _lib.check(L.dense_linear_dgrad_f64(_ptr(g), _ptr(w2d), _ptr(h), _ptr(dz), rows, n_in, n_out, st),
+                   "dense_linear_dgrad_f64")
+        return dz
+
     with torch.cuda.device(dev):
         g4 = gq.contiguous()                                              # [n, 4]
         ev = ready()
-        t3 = torch.mm(g4, w4)
+        g3 = dgrad(g4, w4, a3, n, 64, 4)                                  # [n, 64] incl. the ReLU mask of fc1
         wgrad_aside(ev, g4, a3, gw4, gb4, 4, 64)
-        g3 = relu_grad(t3, a3, 0.0)                                       # [n, 64]
         ev = ready()
-        t2 = torch.mm(g3, w3)
+        g2f = dgrad(g3, w3, a2, n, 256, 64)                               # [n, 256], feature = channel*4 + position
         wgrad_aside(ev, g3, a2, gw3, gb3, 64, 256)
-        g2f = relu_grad(t2, a2, 0.0)                                      # [n, 256], feature = channel*4 + position
         g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
         ev = ready()
-        gp2 = torch.mm(g2, w2.reshape(64, 256))                           # [4n, 256] gradient of the patch matrix
+        gp2 = dgrad(g2, w2.reshape(64, 256), None, 4 * n, 256, 64)        # [4n, 256] gradient of the patch matrix
         wgrad_aside(ev, g2, p2, gw2, gb2, 64, 256)
         # col2im, relu'(conv1) and dW1 / db1 against the boards' cells in one pass (no conv1 gradient tensor)
         scratch = torch.empty(L.conv1_wgrad_fused_scratch_elems(n), **kw)

@@ -56,7 +56,7 @@ __host__ __device__ constexpr int dg_pad(int w) {      // smallest stride >= w t
   return w + ((4 - (w % 16)) + 16) % 16;
 }
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_MASK = 2, EPI_PARTIAL = 3 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_MASK = 2, EPI_PARTIAL = 3, EPI_PLAIN = 4 };
 
 struct DgArgs {
   const double* a;      // A operand
@@ -349,19 +349,35 @@ cudaError_t dg_launch(const DgArgs& p, int splits, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// tile-height choice: the MT in {17, 9, 5} that wastes the fewest SM slots in the last wave
-template <int NTW, bool A_RC, bool B_RC, int EPI>
-cudaError_t dg_dispatch_rows(const DgArgs& p, int sms, cudaStream_t st) {
-  const int col_tiles = (p.cols + 64 * NTW - 1) / (64 * NTW);
-  auto waste = [&](int mt) {
-    const int64_t ctas = (int64_t)((p.rows + 8 * mt - 1) / (8 * mt)) * col_tiles;
-    const int64_t waves = (ctas + sms - 1) / sms;
-    return (double)(waves * sms * mt) / ((double)p.rows / 8.0 * col_tiles);      // SM-time per useful tile row (>= 1)
-  };
-  const double w17 = waste(17), w9 = waste(9), w5 = waste(5);
-  if (w17 <= w9 && w17 <= w5) return dg_launch<17, NTW, A_RC, B_RC, EPI>(p, 1, st);
-  if (w9 <= w5) return dg_launch<9, NTW, A_RC, B_RC, EPI>(p, 1, st);
-  return dg_launch<5, NTW, A_RC, B_RC, EPI>(p, 1, st);
+// tile choice: among heights 8 * {17, 9, 5} and widths 64 * {2, 1} the (MT, NTW) that wastes the fewest SM slots
+// in the last wave (5000 x 512: 136 x 128 tiles = 148 CTAs; 5000 x 256: 136 x 64 tiles = 148 CTAs)
+inline double dg_waste(int rows, int cols, int mt, int ntw, int sms) {
+  const int64_t ctas = (int64_t)((rows + 8 * mt - 1) / (8 * mt)) * ((cols + 64 * ntw - 1) / (64 * ntw));
+  const int64_t waves = (ctas + sms - 1) / sms;
+  // SM-time of the launch relative to the useful work; the narrow tile pays ~6 % more per tile (one A fragment
+  // load per DMMA instead of one per two)
+  return (double)(waves * sms) * mt * ntw * (ntw == 1 ? 1.02 : 1.0) / ((double)rows / 8.0 * ((double)cols / 64.0));
+}
+
+template <bool A_RC, bool B_RC, int EPI>
+cudaError_t dg_dispatch(const DgArgs& p, int sms, cudaStream_t st) {
+  int best_mt = 17, best_ntw = 2;
+  double best = 1e30;
+  for (int ntw = 2; ntw >= 1; --ntw) {
+    if (ntw == 2 && p.cols % 128 != 0 && p.cols > 64) continue;       // keep full column tiles where possible
+    for (int mt : {17, 9, 5}) {
+      const double w = dg_waste(p.rows, p.cols, mt, ntw, sms);
+      if (w < best) { best = w; best_mt = mt; best_ntw = ntw; }
+    }
+  }
+  if (best_ntw == 2) {
+    if (best_mt == 17) return dg_launch<17, 2, A_RC, B_RC, EPI>(p, 1, st);
+    if (best_mt == 9) return dg_launch<9, 2, A_RC, B_RC, EPI>(p, 1, st);
+    return dg_launch<5, 2, A_RC, B_RC, EPI>(p, 1, st);
+  }
+  if (best_mt == 17) return dg_launch<17, 1, A_RC, B_RC, EPI>(p, 1, st);
+  if (best_mt == 9) return dg_launch<9, 1, A_RC, B_RC, EPI>(p, 1, st);
+  return dg_launch<5, 1, A_RC, B_RC, EPI>(p, 1, st);
 }
 
 }  // namespace
@@ -390,35 +406,31 @@ extern "C" int dense_linear_forward_f64(const double* a, const double* w, const 
   }
   if (n_out & 1) return B2048_EINVAL;
   DgArgs p{a, w, c, bias, nullptr, 0, n_in, n_in, n_out, (int)rows, n_out, n_in, ((n_in + DG_RC - 1) / DG_RC) * DG_RC};
-  cudaError_t e;
-  if (n_out % 128 == 0)
-    e = relu ? dg_dispatch_rows<2, true, true, EPI_BIAS_RELU>(p, ctx->sm_count, st)
-             : dg_dispatch_rows<2, true, true, EPI_BIAS>(p, ctx->sm_count, st);
-  else
-    e = relu ? dg_dispatch_rows<1, true, true, EPI_BIAS_RELU>(p, ctx->sm_count, st)
-             : dg_dispatch_rows<1, true, true, EPI_BIAS>(p, ctx->sm_count, st);
+  const cudaError_t e = relu ? dg_dispatch<true, true, EPI_BIAS_RELU>(p, ctx->sm_count, st)
+                             : dg_dispatch<true, true, EPI_BIAS>(p, ctx->sm_count, st);
   return (int)e;
 }
 
 // dz_in[rows x n_in] = (G[rows x n_out] W[n_out x n_in]) * (H[rows x n_in] > 0): input gradient of a Linear layer
-// fused with the ReLU mask of the layer below (H = that layer's output).
+// fused with the ReLU mask of the layer below (H = that layer's output); h == NULL: no mask (plain G W).
 extern "C" int dense_linear_dgrad_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows,
                                       int n_in, int n_out, void* stream) {
-  if (!g || !w || !h || !dz || rows <= 0 || n_in <= 0 || n_out <= 0 || rows > (1 << 30)) return B2048_EINVAL;
+  if (!g || !w || !dz || rows <= 0 || n_in <= 0 || n_out <= 0 || rows > (1 << 30)) return B2048_EINVAL;
   if ((n_in & 1) || (n_out & 1) || ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(w) |
                                      reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dz)) & 15u))
     return B2048_EINVAL;
   DG_CTX();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_out == 4) {
+    if (!h) return B2048_EINVAL;
     const int64_t total = rows * n_in;
     dense_out4_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, w, h, dz, total, n_in);
     return (int)cudaGetLastError();
   }
   // C(i = row, j = input unit) = sum_r G(i, r) W(r, j): A reduction-contiguous, B reduction-strided
   DgArgs p{g, w, dz, h, nullptr, 0, n_out, n_in, n_in, (int)rows, n_in, n_out, ((n_out + DG_RC - 1) / DG_RC) * DG_RC};
-  cudaError_t e = (n_in % 128 == 0) ? dg_dispatch_rows<2, true, false, EPI_MASK>(p, ctx->sm_count, st)
-                                    : dg_dispatch_rows<1, true, false, EPI_MASK>(p, ctx->sm_count, st);
+  const cudaError_t e = h ? dg_dispatch<true, false, EPI_MASK>(p, ctx->sm_count, st)
+                          : dg_dispatch<true, false, EPI_PLAIN>(p, ctx->sm_count, st);
   return (int)e;
 }
 
