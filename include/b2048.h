@@ -162,6 +162,26 @@ int b2048_random_boards(uint64_t* boards, int64_t n, uint64_t seed, uint64_t ind
 int b2048_random_actions(uint8_t* actions, int64_t n, uint64_t seed, uint64_t step,
                          uint64_t index_base, void* stream);
 
+/* ONE board per call, host data in and out: the engine behind the drop-in `board.Board2048` (BASELINE config 1:
+ * player.py's loop calls the board one at a time).  One kernel launch and one stream synchronisation per call:
+ * the 16 tile values travel as a kernel argument, the result is written to mapped pinned memory.
+ *   op 0 MOVE  : next[0] = move of `tiles16` by `action` (+ spawn iff spawn != 0 and the board changed), reward[0],
+ *                flags = B2048_FLAG_* of b2048_step                       (src/board.py:147-202)
+ *   op 1 ALL4  : next[a], reward[a] for the four actions, flags as b2048_step_all4   (src/board.py:138-145)
+ *   op 2 LEGAL : flags = legal mask | done                                 (src/board.py:128-135)
+ *   op 3 SPAWN : next[0] = tiles16 with one spawned tile                   (src/board.py:41-51)
+ *   op 4 FRESH : next[0] = a fresh board (two spawns; tiles16 ignored)     (src/board.py:10-20)
+ * Same arithmetic and Philox lanes as the batched entry points with n = 1, index_base = 0.  result->bad != 0:
+ * a tile value was not 0 or a power of two in 2..32768 (nothing else is written).  Calls on one device serialise. */
+typedef struct b2048_board_result {
+  int64_t next[4][16];
+  int32_t reward[4];
+  uint32_t flags;
+  uint32_t bad;
+} b2048_board_result;
+int b2048_board_host(int op, const int64_t* tiles16, int action, int spawn, uint64_t seed, uint64_t step,
+                     uint32_t p4_threshold, b2048_board_result* result, int device);
+
 /* Pinned host memory for b2048_step_host, placed on the NUMA node next to `device`: the calling thread is
  * bound to the GPU's local CPUs (sysfs local_cpulist) while the pages are allocated and first touched, then
  * its affinity is restored.  *numa_node_out = that node (-1 unknown), *bound_out = 1 if the binding was

@@ -23,6 +23,12 @@ class Ring(ctypes.Structure):
                 ("head_size", c_void_p), ("capacity", c_int64)]
 
 
+class BoardResult(ctypes.Structure):
+    """struct b2048_board_result (include/b2048.h)."""
+    _fields_ = [("next", (ctypes.c_int64 * 16) * 4), ("reward", ctypes.c_int32 * 4), ("flags", ctypes.c_uint32),
+                ("bad", ctypes.c_uint32)]
+
+
 # symbol -> (restype, argtypes); must list every function include/b2048.h declares
 SIGNATURES = {
     "b2048_init": (c_int, [c_int]),
@@ -45,6 +51,7 @@ SIGNATURES = {
     "b2048_random_actions": (c_int, [c_void_p, c_int64, c_uint64, c_uint64, c_uint64, c_void_p]),
     "b2048_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_uint64,
                                 c_uint64, c_uint64, c_uint32, c_void_p, c_int]),
+    "b2048_board_host": (c_int, [c_int, c_void_p, c_int, c_int, c_uint64, c_uint64, c_uint32, c_void_p, c_int]),
     "b2048_host_alloc": (c_int, [ctypes.POINTER(c_void_p), ctypes.c_size_t, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "b2048_host_free": (c_int, [c_void_p]),
     "b2048_bind_thread_near": (c_int, [c_int]),

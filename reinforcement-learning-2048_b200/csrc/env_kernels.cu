@@ -11,6 +11,9 @@
 // per four boards.  Small batches use `step_small_kernel`, which reads the L2-resident table
 // directly and so skips the 224 KB staging.
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "b2048_common.cuh"
 
@@ -776,6 +779,79 @@ __global__ void random_actions_kernel(uint8_t* __restrict__ actions, int64_t n, 
   actions[i] = (uint8_t)(w >> 30);
 }
 
+// ---- one board per call: the engine behind the drop-in board.Board2048 (BASELINE config 1) --------------------------
+// Board2048.peek_action / available_moves / available_moves_as_torch_unit_vector / _populate_empty_cell / __init__
+// (src/board.py:10-20, 41-51, 128-202) for ONE board: tile values come in as a kernel argument, the result goes to
+// mapped pinned host memory -- one launch and one stream synchronisation per call, no copies, no allocation.
+// Same arithmetic (and the same Philox lanes: global index 0) as the batched kernels with n = 1.
+struct SingleIn {
+  int64_t tiles[16];
+};
+struct SingleOut {          // mirrors struct b2048_board_result of include/b2048.h
+  int64_t next[4][16];
+  int32_t reward[4];
+  uint32_t flags;
+  uint32_t bad;
+};
+enum : int { SB_MOVE = 0, SB_ALL4 = 1, SB_LEGAL = 2, SB_SPAWN = 3, SB_FRESH = 4 };
+
+__device__ __forceinline__ void unpack16(uint32_t lo, uint32_t hi, int64_t* t) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const uint32_t e = ((c < 8 ? lo : hi) >> (4 * (c & 7))) & 0xFu;
+    t[c] = e ? ((int64_t)1 << e) : 0;
+  }
+}
+
+__global__ void single_board_kernel(const SingleIn in, int op, int action, int spawn, uint64_t seed, uint64_t step,
+                                    uint32_t p4, const uint32_t* __restrict__ glut, SingleOut* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  uint32_t lo = 0, hi = 0, bad = 0;
+  if (op != SB_FRESH) {
+    for (int c = 0; c < 16; ++c) {
+      const int64_t t = in.tiles[c];
+      uint32_t e = 0;
+      if (t != 0) {
+        if (t < 2 || t > 32768 || (t & (t - 1)) != 0) bad = 1;
+        else e = 63u - (uint32_t)__clzll(t);
+      }
+      if (c < 8) lo |= e << (4 * c);
+      else hi |= e << (4 * (c - 8));
+    }
+  }
+  out->bad = bad;
+  if (bad) return;
+  const uint32_t D = spawn_draw_of(seed, step, 0);
+  if (op == SB_MOVE) {
+    uint32_t nl, nh, rw, f, ch;
+    slide_board<true>(lo, hi, (uint32_t)action & 3u, nullptr, glut, nl, nh, rw, f, ch);
+    if (spawn) finish_board<false>(nl, nh, ch, D, p4, 0xFFu, f);
+    unpack16(nl, nh, out->next[0]);
+    out->reward[0] = (int32_t)rw;
+    out->flags = f;
+  } else if (op == SB_ALL4) {
+    uint32_t nl[4], nh[4], rw[4], f;
+    all4_board<false>(lo, hi, nullptr, glut, D, p4, 0xFFFFFFFFu, nl, nh, rw, f);
+    for (int a = 0; a < 4; ++a) {
+      unpack16(nl[a], nh[a], out->next[a]);
+      out->reward[a] = (int32_t)rw[a];
+    }
+    out->flags = f;
+  } else if (op == SB_LEGAL) {
+    const uint32_t m = legal_mask(lo, hi);
+    out->flags = m | (m ? 0u : (uint32_t)B2048_FLAG_DONE);
+  } else if (op == SB_SPAWN) {
+    if ((lo | hi) == 0) spawn_at(lo, hi, D >> 28, ((D << 4) < p4) ? 2u : 1u);
+    else spawn_draw16(lo, hi, D, p4, 1u);
+    unpack16(lo, hi, out->next[0]);
+    out->flags = 0;
+  } else {
+    const uint64_t b = fresh_board(seed, step, 0, p4);
+    unpack16((uint32_t)b, (uint32_t)(b >> 32), out->next[0]);
+    out->flags = 0;
+  }
+}
+
 inline int64_t blocks_for(int64_t n, int threads) { return (n + threads - 1) / threads; }
 
 // Batches at or above this many boards use the persistent shared-memory-table kernel.
@@ -1041,6 +1117,46 @@ extern "C" int b2048_random_actions(uint8_t* actions, int64_t n, uint64_t seed, 
   random_actions_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       actions, n, seed, step, index_base);
   return (int)cudaGetLastError();
+}
+
+// ---- one-board host call -------------------------------------------------------------------------------------------
+namespace {
+struct SingleSlot {
+  SingleOut* host = nullptr;     // mapped pinned memory: the kernel writes the result straight into it
+  SingleOut* dev = nullptr;
+  cudaStream_t stream = nullptr;
+};
+SingleSlot g_single[MAX_DEVICES];
+std::mutex g_single_mu[MAX_DEVICES];
+}  // namespace
+
+extern "C" int b2048_board_host(int op, const int64_t* tiles16, int action, int spawn, uint64_t seed, uint64_t step,
+                                uint32_t p4_threshold, b2048_board_result* result, int device) {
+  if (op < SB_MOVE || op > SB_FRESH || !result || (op != SB_FRESH && !tiles16)) return B2048_EINVAL;
+  DeviceCtx* c = ctx_for(device);
+  if (!c || !c->ready) return B2048_ENOTINIT;
+  static_assert(sizeof(b2048_board_result) == sizeof(SingleOut), "b2048_board_result mirrors SingleOut");
+  std::lock_guard<std::mutex> lock(g_single_mu[device]);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  SingleSlot& sl = g_single[device];
+  if (!sl.host) {
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&sl.host), sizeof(SingleOut), cudaHostAllocMapped)) != cudaSuccess)
+      return (int)e;
+    if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&sl.dev), sl.host, 0)) != cudaSuccess) return (int)e;
+    if ((e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+  }
+  SingleIn in;
+  if (op != SB_FRESH) memcpy(in.tiles, tiles16, sizeof(in.tiles));
+  else memset(in.tiles, 0, sizeof(in.tiles));
+  single_board_kernel<<<1, 32, 0, sl.stream>>>(in, op, action, spawn, seed, step, p4_threshold, c->lut, sl.dev);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(sl.stream);
+  if (e == cudaSuccess) memcpy(result, sl.host, sizeof(SingleOut));
+  cudaSetDevice(prev);
+  return (int)e;
 }
 
 // used by host_api.cu (b2048_step_host)
