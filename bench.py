@@ -14,8 +14,12 @@ GPU (torchrun); boards are sharded by contiguous global index, there is no data-
 One JSON line is printed by rank 0 (see the bench contract in the task statement): `value` is
 measured with inputs resident in HBM, `e2e` through the host-buffer C-ABI call (b2048_step_host)
 with pinned host memory and both copies inside the timed region, `roofline` against the measured
-HBM copy bandwidth in MEASURED_PEAKS.json, `cpu_baseline` the C port of the reference algorithm
-(oracle/board_oracle.c) on the host cores of the same box.
+HBM copy bandwidth in MEASURED_PEAKS.json (and, as `frac_vs_spec`, against the 8 TB/s of north_star),
+`cpu_baseline` the C port of the reference algorithm (oracle/board_oracle.c) on the host cores of the
+same box.  BASELINE.json's second metric, Double-DQN updates/sec at batch 5000, is the `ddqn` block
+(conv + dense, fraction of the measured FP64 tensor-core peak, the unmodified reference's train_step on
+this host beside it, replica identity at N > 1); `extra` carries config 2, config 5, the steady-state
+distribution, rollouts, the end-to-end trainer, the link probe and the reference's own CPU figures.
 """
 from __future__ import annotations
 
@@ -536,7 +540,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "boards_per_gpu": n, "p_four": 0.1,
                        "l2": "inputs+outputs 1.4 GB/step >> 126 MB L2 (no flush needed)",
                        "parallelism": f"env-shard x{world} (no data-path collective)",
-                       "timing": "CUDA events on torch's current stream (the launch stream); max over ranks"},
+                       "timing": "two CUDA events around the K back-to-back launches on torch's current stream (the launch stream); max over ranks"},
             "clocks": clocks,
             "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "steps/s",
                     "h2d_bytes_per_step": n * 9, "d2h_bytes_per_step": n * 13, "steps": e2e_steps,
