@@ -310,6 +310,12 @@ int dense_linear_forward_f64(const double* a, const double* w, const double* bia
  * h == NULL gives the plain product (the conv Q-network's patch-matrix gradient, masked later). */
 int dense_linear_dgrad_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows, int n_in,
                            int n_out, void* stream);
+/* The same product with the result regrouped: input unit j = c * group + t of row i is stored at row i * group + t,
+ * column c of dz [rows * group, n_in / group] (group even, n_in % group == 0, h required).  For the layer behind
+ * nn.Flatten of a [channels, positions] map (src/configs/double_dqn_conv.py:24-25) with group = positions this
+ * writes the gradient directly as the (board, position) x channel row matrix the convolution's backward reads. */
+int dense_linear_dgrad_regroup_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows,
+                                   int n_in, int n_out, int group, void* stream);
 /* Weight and bias gradient: dw[n_out, n_in] = g^T x, db[n_out] = column sums of g over `rows` rows (x = the layer's
  * input).  The rows are split over the SMs; per-split products go to `scratch`
  * (dense_linear_wgrad_scratch_elems(rows, n_in, n_out) doubles, 16-byte aligned) and are added in a fixed order,
@@ -359,6 +365,19 @@ int qnet_conv_forward_train_f64(const double* states, const double* w1, const do
                                 const double* b4, double* q, double* patches2, double* act2, double* act3,
                                 int64_t n, void* stream);
 
+/* The three forwards of ONE Double-DQN update as a single launch (src/dqn_lib.py:126-128 and :146):
+ *   q[n,4] = online(states) + patches2 / act2 / act3 as qnet_conv_forward_train_f64 stores them,
+ *   q_next_online[n,4] = online(next_states)   (NULL for plain DQN),
+ *   q_next_target[n,4] = target(next_states).
+ * online / target: the eight parameter pointers {w1, b1, w2, b2, w3, b3, w4, b4} of each network.  The SMs are
+ * divided between the two weight sets in proportion to their boards and every CTA gets the same share, so a
+ * batch of 5 000 runs as 104 boards on each of 146 SMs instead of three 125-CTA launches queueing for the
+ * same SMs.  Results are bit-identical to the separate calls. */
+int qnet_conv_forward_update_f64(const double* states, const double* next_states, const double* const* online,
+                                 const double* const* target, double* q, double* patches2, double* act2,
+                                 double* act3, double* q_next_online, double* q_next_target, int64_t n,
+                                 void* stream);
+
 /* ---- weight + bias gradient of a layer with a tiny weight matrix ----------------------------------- */
 
 /* In train_step's backward (src/dqn_lib.py:159-161): dW[c][k] = sum_r g[r][c] * x[r][k] and
@@ -390,6 +409,15 @@ int layer_wgrad64_f64(const double* g, const double* x, double* dw, double* db, 
 int64_t conv1_wgrad_fused_scratch_elems(int64_t n);
 int conv1_wgrad_fused_f64(const double* gpatches2, const double* patches2, const double* states, double* dw1,
                           double* db1, double* scratch, int64_t n, void* stream);
+
+/* The same backward straight from g2 = d loss / d (conv2 pre-activation) [4n,64] (rows (board, position)): the
+ * patch-matrix gradient g2 w2 (w2 = conv2.weight as [64,256]) stays in the tensor-core accumulators and is
+ * consumed in place — mask, dW1, db1 — so neither it nor the conv1 gradient ever exists in memory.  One DMMA
+ * kernel + the fixed-order sum of its per-CTA partial results.  g2, patches2 16-byte aligned.
+ * scratch: conv2_dgrad_conv1_wgrad_scratch_elems(n) doubles. */
+int64_t conv2_dgrad_conv1_wgrad_scratch_elems(int64_t n);
+int conv2_dgrad_conv1_wgrad_f64(const double* g2, const double* w2, const double* patches2, const double* states,
+                                double* dw1, double* db1, double* scratch, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,7 @@ SIGNATURES = {
                                        ctypes.c_double, c_void_p]),
     "dense_linear_forward_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "dense_linear_dgrad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dense_linear_dgrad_regroup_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "dense_linear_wgrad_scratch_elems": (c_int64, [c_int64, c_int, c_int]),
     "dense_linear_wgrad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "egreedy_select": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_uint64, c_uint64, c_uint64,
@@ -82,8 +83,11 @@ SIGNATURES = {
     "layer_wgrad64_scratch_elems": (c_int64, [c_int64, c_int]),
     "layer_wgrad64_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "qnet_conv_forward_train_f64": (c_int, [c_void_p] * 13 + [c_int64, c_void_p]),
+    "qnet_conv_forward_update_f64": (c_int, [c_void_p] * 10 + [c_int64, c_void_p]),
     "conv1_wgrad_fused_scratch_elems": (c_int64, [c_int64]),
     "conv1_wgrad_fused_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "conv2_dgrad_conv1_wgrad_scratch_elems": (c_int64, [c_int64]),
+    "conv2_dgrad_conv1_wgrad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "qnet_conv_forward_f64": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_void_p, c_int64, c_void_p]),
 }
 

@@ -104,6 +104,28 @@ def conv_q_forward_saving(x, params):
     return q, (x, p2, a2, a3)
 
 
+def conv_q_forward_update(x, x_next, params, target_params, want_online_next=True):
+    """The forwards of one Double-DQN update as ONE K6 launch (`qnet_conv_forward_update_f64`): Q(s) of the
+    online network with saved activations, Q(s') of the online network (optional) and Q(s') of the target.
+    -> (q, saved, q_next_online | None, q_next_target); bit-identical to the three separate launches."""
+    import ctypes
+    n = x.shape[0]
+    dev = _dev(x)
+    _lib.init(dev)
+    kw = dict(dtype=torch.float64, device=x.device)
+    q, p2 = torch.empty((n, 4), **kw), torch.empty((4 * n, 256), **kw)
+    a2, a3 = torch.empty((n, 256), **kw), torch.empty((n, 64), **kw)
+    qno = torch.empty((n, 4), **kw) if want_online_next else None
+    qnt = torch.empty((n, 4), **kw)
+    arr = ctypes.c_void_p * 8
+    on, tg = arr(*[_ptr(p) for p in params]), arr(*[_ptr(p) for p in target_params])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qnet_conv_forward_update_f64(_ptr(x), _ptr(x_next), on, tg, _ptr(q), _ptr(p2), _ptr(a2), _ptr(a3),
+                                                           _ptr(qno) if qno is not None else None, _ptr(qnt), n, _stream(x)),
+                   "qnet_conv_forward_update_f64")
+    return q, (x, p2, a2, a3), qno, qnt
+
+
 def conv_q_backward(saved, params, gq, out=None):
     """Gradients of the eight parameter tensors given gq = d loss / d q [n,4]: per layer the K7 weight /
     bias gradient kernels on the saved matrices (on a side stream: they are leaves of the dependency chain
@@ -158,16 +180,18 @@ def conv_q_backward(saved, params, gq, out=None):
         g3 = dgrad(g4, w4, a3, n, 64, 4)                                  # [n, 64] incl. the ReLU mask of fc1
         wgrad_aside(ev, g4, a3, gw4, gb4, 4, 64)
         ev = ready()
-        g2f = dgrad(g3, w3, a2, n, 256, 64)                               # [n, 256], feature = channel*4 + position
+        # fc1's input gradient, written directly as rows (board, position) x channel (feature = channel*4 + position)
+        g2 = torch.empty((4 * n, 64), **kw)
+        _lib.check(L.dense_linear_dgrad_regroup_f64(_ptr(g3), _ptr(w3), _ptr(a2), _ptr(g2), n, 256, 64, 4, st),
+                   "dense_linear_dgrad_regroup_f64")
         wgrad_aside(ev, g3, a2, gw3, gb3, 64, 256)
-        g2 = g2f.view(n, 64, 4).transpose(1, 2).reshape(4 * n, 64)        # rows (board, position) x channel
         ev = ready()
-        gp2 = dgrad(g2, w2.reshape(64, 256), None, 4 * n, 256, 64)        # [4n, 256] gradient of the patch matrix
+        # conv2's input gradient (g2 W2, the gradient of the patch matrix) never leaves the tensor-core accumulators:
+        # relu'(conv1), dW1 and db1 against the boards' cells are taken from them in the same kernel
+        scratch = torch.empty(L.conv2_dgrad_conv1_wgrad_scratch_elems(n), **kw)
+        _lib.check(L.conv2_dgrad_conv1_wgrad_f64(_ptr(g2), _ptr(w2), _ptr(p2), _ptr(x), _ptr(gw1), _ptr(gb1), _ptr(scratch),
+                                                 n, st), "conv2_dgrad_conv1_wgrad_f64")
         wgrad_aside(ev, g2, p2, gw2, gb2, 64, 256)
-        # col2im, relu'(conv1) and dW1 / db1 against the boards' cells in one pass (no conv1 gradient tensor)
-        scratch = torch.empty(L.conv1_wgrad_fused_scratch_elems(n), **kw)
-        _lib.check(L.conv1_wgrad_fused_f64(_ptr(gp2), _ptr(p2), _ptr(x), _ptr(gw1), _ptr(gb1), _ptr(scratch), n, st),
-                   "conv1_wgrad_fused_f64")
         main.wait_stream(side)
     return out
 
@@ -220,6 +244,12 @@ class TrainableConvQ(nn.Module):
     def forward_saving(self, x: torch.Tensor):
         """Q(s) plus the activations `backward_into` needs, outside autograd (DDQNUpdater's direct path)."""
         return conv_q_forward_saving(x.reshape(x.shape[0], 16), self.params())
+
+    @torch.no_grad()
+    def forward_update(self, x: torch.Tensor, x_next: torch.Tensor, target: "TrainableConvQ", use_double: bool = True):
+        """Every forward of one update in one launch: -> (Q(s), saved, Q_online(s') | None, Q_target(s'))."""
+        return conv_q_forward_update(x.reshape(x.shape[0], 16), x_next.reshape(x_next.shape[0], 16), self.params(),
+                                     target.params(), want_online_next=use_double)
 
     @torch.no_grad()
     def backward_into(self, saved, gq: torch.Tensor, grads) -> None:

@@ -68,29 +68,35 @@ class DDQNUpdater:
     def _update_eager(self):
         states, actions, rewards, next_states, dones = self.ring.sample(self.B, seed=self.seed, ctr=ReplayRing.CTR_AUTO,
                                                                         out=self.batch)
-        # the two no-grad forwards run on side streams next to the autograd forward (the kernels
-        # are small; the fork/join is captured into the CUDA graph)
         main = torch.cuda.current_stream(self.device)
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side), torch.no_grad():
-            q_next_target = self._infer(self.i_target, next_states)
-        q_next_online = None
-        if self.use_double:      # its own stream: a short K6 launch leaves most SMs free after its first round
-            self.side2.wait_stream(main)
-            with torch.cuda.stream(self.side2), torch.no_grad():
-                q_next_online = self._infer(self.i_model, next_states)
         direct = hasattr(self.f_model, "forward_saving")       # conv (K6/K7) and dense (K8) configs: no autograd graph at all
-        if direct:
-            q_cur, saved = self.f_model.forward_saving(states)
+        if hasattr(self.f_model, "forward_update") and type(self.f_target) is type(self.f_model) \
+                and states.is_contiguous() and next_states.is_contiguous():
+            # conv config: Q(s) (+ saved activations), Q_online(s') and Q_target(s') are ONE K6 launch
+            q_cur, saved, q_next_online, q_next_target = self.f_model.forward_update(states, next_states, self.f_target,
+                                                                                     self.use_double)
         else:
-            q_cur = self.f_model(self._shape(states))
-        main.wait_stream(self.side)
-        if self.use_double:
-            main.wait_stream(self.side2)
-        if not torch.cuda.is_current_stream_capturing():      # eager mode: tell the allocator about the hand-over
-            q_next_target.record_stream(main)
-            if q_next_online is not None:
-                q_next_online.record_stream(main)
+            # the two no-grad forwards run on side streams next to the training forward (the fork/join is
+            # captured into the CUDA graph)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side), torch.no_grad():
+                q_next_target = self._infer(self.i_target, next_states)
+            q_next_online = None
+            if self.use_double:      # its own stream: a short launch leaves most SMs free after its first round
+                self.side2.wait_stream(main)
+                with torch.cuda.stream(self.side2), torch.no_grad():
+                    q_next_online = self._infer(self.i_model, next_states)
+            if direct:
+                q_cur, saved = self.f_model.forward_saving(states)
+            else:
+                q_cur = self.f_model(self._shape(states))
+            main.wait_stream(self.side)
+            if self.use_double:
+                main.wait_stream(self.side2)
+            if not torch.cuda.is_current_stream_capturing():      # eager mode: tell the allocator about the hand-over
+                q_next_target.record_stream(main)
+                if q_next_online is not None:
+                    q_next_online.record_stream(main)
         if direct:
             # K3 also emits d loss / d Q(s,.); K7 writes every parameter gradient straight into the flat
             # buffer (overwrite: no zeroing, no per-parameter accumulate kernels)

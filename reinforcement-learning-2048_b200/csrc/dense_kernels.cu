@@ -70,6 +70,8 @@ struct DgArgs {
   int rows, cols;       // output extent
   int red;              // reduction extent
   int red_per_split;    // reduction elements per split (multiple of DG_RC); = red rounded up when not split
+  int tgroup;           // EPI_MASK only: 0 = C as it is; T > 0 = column j = c * T + t of row i goes to row i * T + t, column c
+                        // of a [rows * T, cols / T] matrix (nn.Flatten order -> one row per (board, position))
 };
 
 // A_RC / B_RC: the operand is "reduction-contiguous" in global memory:
@@ -249,6 +251,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgemm_dmma_kernel(const DgArgs 
         const double2 h = *reinterpret_cast<const double2*>(p.aux + (int64_t)i * p.ldc + j);
         v0 = h.x > 0.0 ? v0 : 0.0;
         v1 = h.y > 0.0 ? v1 : 0.0;
+        if (p.tgroup) {                            // T is even and j is even: j, j + 1 share c
+          const int t = j % p.tgroup, w = p.cols / p.tgroup;
+          double* o = cbase + ((int64_t)i * p.tgroup + t) * w + j / p.tgroup;
+          o[0] = v0;
+          o[w] = v1;
+          continue;
+        }
       }
       *reinterpret_cast<double2*>(cbase + (int64_t)i * p.ldc + j) = make_double2(v0, v1);
     }
@@ -383,6 +392,10 @@ cudaError_t dg_dispatch(const DgArgs& p, int sms, cudaStream_t st) {
 }  // namespace
 }  // namespace b2048
 
+namespace b2048 {
+int dgrad64x256_masked(const double* g, const double* w, const double* h, double* out, int64_t rows, int group,
+                       cudaStream_t st);                                  // wgrad_kernels.cu
+}
 using namespace b2048;
 
 #define DG_CTX()                         \
@@ -405,7 +418,7 @@ extern "C" int dense_linear_forward_f64(const double* a, const double* w, const 
     return (int)cudaGetLastError();
   }
   if (n_out & 1) return B2048_EINVAL;
-  DgArgs p{a, w, c, bias, nullptr, 0, n_in, n_in, n_out, (int)rows, n_out, n_in, ((n_in + DG_RC - 1) / DG_RC) * DG_RC};
+  DgArgs p{a, w, c, bias, nullptr, 0, n_in, n_in, n_out, (int)rows, n_out, n_in, ((n_in + DG_RC - 1) / DG_RC) * DG_RC, 0};
   const cudaError_t e = relu ? dg_dispatch<true, true, EPI_BIAS_RELU>(p, ctx->sm_count, st)
                              : dg_dispatch<true, true, EPI_BIAS>(p, ctx->sm_count, st);
   return (int)e;
@@ -413,9 +426,10 @@ extern "C" int dense_linear_forward_f64(const double* a, const double* w, const 
 
 // dz_in[rows x n_in] = (G[rows x n_out] W[n_out x n_in]) * (H[rows x n_in] > 0): input gradient of a Linear layer
 // fused with the ReLU mask of the layer below (H = that layer's output); h == NULL: no mask (plain G W).
-extern "C" int dense_linear_dgrad_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows,
-                                      int n_in, int n_out, void* stream) {
+static int dgrad_impl(const double* g, const double* w, const double* h, double* dz, int64_t rows, int n_in, int n_out,
+                      int tgroup, void* stream) {
   if (!g || !w || !dz || rows <= 0 || n_in <= 0 || n_out <= 0 || rows > (1 << 30)) return B2048_EINVAL;
+  if (tgroup && (!h || n_out == 4 || tgroup < 2 || (tgroup & 1) || n_in % tgroup)) return B2048_EINVAL;
   if ((n_in & 1) || (n_out & 1) || ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(w) |
                                      reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(dz)) & 15u))
     return B2048_EINVAL;
@@ -427,11 +441,28 @@ extern "C" int dense_linear_dgrad_f64(const double* g, const double* w, const do
     dense_out4_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, w, h, dz, total, n_in);
     return (int)cudaGetLastError();
   }
+  // a masked 64 -> 256 layer (fc1 of the conv Q-network): reduction too short for the pipelined tiles
+  if (h && n_out == 64 && n_in == 256 && (tgroup == 0 || 256 % tgroup == 0)) return dgrad64x256_masked(g, w, h, dz, rows, tgroup, st);
   // C(i = row, j = input unit) = sum_r G(i, r) W(r, j): A reduction-contiguous, B reduction-strided
-  DgArgs p{g, w, dz, h, nullptr, 0, n_out, n_in, n_in, (int)rows, n_in, n_out, ((n_out + DG_RC - 1) / DG_RC) * DG_RC};
+  DgArgs p{g, w, dz, h, nullptr, 0, n_out, n_in, n_in, (int)rows, n_in, n_out, ((n_out + DG_RC - 1) / DG_RC) * DG_RC, tgroup};
   const cudaError_t e = h ? dg_dispatch<true, false, EPI_MASK>(p, ctx->sm_count, st)
                           : dg_dispatch<true, false, EPI_PLAIN>(p, ctx->sm_count, st);
   return (int)e;
+}
+
+extern "C" int dense_linear_dgrad_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows,
+                                      int n_in, int n_out, void* stream) {
+  return dgrad_impl(g, w, h, dz, rows, n_in, n_out, 0, stream);
+}
+
+// The same product with the result regrouped: input unit j = c * group + t of row i is stored at row i * group + t,
+// column c of dz [rows * group, n_in / group].  For a layer that follows nn.Flatten of a [C, positions] map
+// (src/configs/double_dqn_conv.py:24-25) with group = positions this writes the gradient as the row matrix
+// (board, position) x channel the convolution's GEMM-form backward consumes: no transpose pass.
+extern "C" int dense_linear_dgrad_regroup_f64(const double* g, const double* w, const double* h, double* dz, int64_t rows,
+                                              int n_in, int n_out, int group, void* stream) {
+  if (group <= 0) return B2048_EINVAL;
+  return dgrad_impl(g, w, h, dz, rows, n_in, n_out, group, stream);
 }
 
 // splits and scratch of the weight gradient for (rows, n_in, n_out)

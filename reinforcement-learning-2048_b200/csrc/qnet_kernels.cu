@@ -86,10 +86,33 @@ struct QConvSaved {
   double* act2;       // [n, 256]:  relu(conv2) in nn.Flatten order (channel*4 + position)
   double* act3;       // [n, 64]:   relu(fc1)
 };
+// One launch = up to two networks (weight sets), each with its own CTAs, each evaluating up to two batches
+// ("jobs").  The unit of work is a PAIR TILE: the 4 * MT boards one warp pair carries through the network.  A
+// network's jobs are laid end to end in pair tiles; its CTAs split that range into equal contiguous pieces, and
+// within a CTA pair p takes tiles lo + p, lo + p + PAIRS, ...  A plain forward is one network with one job; the
+// Double-DQN update (src/dqn_lib.py:126-128, :146) is {online: Q(s) saving, Q(s')} + {target: Q(s')} in one
+// launch: 15 000 boards spread evenly over all SMs instead of three 125-CTA launches that run one after the other.
+struct QJob {
+  const uint64_t* boards;   // packed boards, or
+  const double* states;     // float64 [n,16]
+  double* q;
+  QConvSaved sv;            // SAVE instantiation: patches2 == nullptr -> this job stores nothing
+  int64_t n;
+  int64_t pt0;              // first pair tile of the job in its network's range
+};
+struct QNet {
+  QConvWeights w;
+  int cta0, ctas;           // this network's CTAs: [cta0, cta0 + ctas)
+  int job0, njobs;          // its jobs: job[job0 .. job0 + njobs)
+  int64_t pts, per;         // pair tiles in total / per CTA
+};
+struct QLaunch {
+  QNet net[2];
+  QJob job[4];
+  int nnets, scaling;
+};
 template <int MT, int PAIRS, bool SAVE>
-__global__ void __launch_bounds__(64 * PAIRS, 1)
-    qconv_forward_kernel(const uint64_t* __restrict__ boards, const double* __restrict__ states, int scaling,
-                         const QConvWeights wts, double* __restrict__ q, int64_t n, const QConvSaved sv) {
+__global__ void __launch_bounds__(64 * PAIRS, 1) qconv_forward_kernel(const QLaunch m) {
   extern __shared__ __align__(16) unsigned char qsm[];
   using S = QS<PAIRS>;
   constexpr int QC_THREADS = 64 * PAIRS;
@@ -104,6 +127,10 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, wip = warp & 1;
   const int fr = lane >> 2, fk = lane & 3;     // fragment row (A, C) / column (B) and k index
+  const int ni = (m.nnets > 1 && (int)blockIdx.x >= m.net[1].cta0) ? 1 : 0;
+  const QNet& net = m.net[ni];
+  const QConvWeights wts = net.w;
+  const int scaling = m.scaling;
 
   // ---- stage the weights: conv2 in B-fragment order, the small ones as they are --------------------
   // B fragment of mma.m8n8k4 (col): lane holds B[k = lane % 4][n = lane / 4];  k-step = c1, k = tap,
@@ -138,19 +165,30 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
   double* in2p = in2 + pair * 8 * IN2_STRIDE;
   double* qpartp = qpart + pair * 32;
 
-  constexpr int TILE = 4 * MT * PAIRS;                 // boards per CTA iteration, 2 * MT per warp
-  const int64_t tiles = (n + TILE - 1) / TILE;
+  constexpr int PT = 4 * MT;                           // boards per pair tile, 2 * MT per warp
+  const int64_t pt_lo = (int64_t)((int)blockIdx.x - net.cta0) * net.per;
+  const int64_t pt_hi = pt_lo + net.per < net.pts ? pt_lo + net.per : net.pts;
 #if QC_STAGGER
   // Each scheduler hosts one warp of pairs 0/1 and one of pairs 2/3.  Left alone they run conv2 (DMMA
   // bound) and epilogue + fc1 (latency bound) in lockstep; starting pairs 2/3 a third of a tile later
   // lets one warp's DMMA stream cover the other's epilogue.  Only worth it for long launches.
-  if (PAIRS == 4 && pair >= 2 && tiles >= 8 * (int64_t)gridDim.x) {
+  if (PAIRS == 4 && pair >= 2 && net.per >= 8 * PAIRS) {
     const long long t0 = clock64();
     while (clock64() - t0 < QC_STAGGER) {}
   }
 #endif
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t s_warp = tile * TILE + warp * (2 * MT);   // first of this warp's boards
+  for (int64_t pt = pt_lo + pair; pt < pt_hi; pt += PAIRS) {
+    // the job this pair tile belongs to (at most two per network) and the tile's first board in it
+    const int ji = net.job0 + ((net.njobs > 1 && pt >= m.job[net.job0 + 1].pt0) ? 1 : 0);
+    const QJob& job = m.job[ji];
+    const uint64_t* __restrict__ boards = job.boards;
+    const double* __restrict__ states = job.states;
+    double* __restrict__ q = job.q;
+    const QConvSaved sv = job.sv;
+    const bool save = SAVE && sv.patches2 != nullptr;
+    const int64_t n = job.n;
+    const int64_t s_pair = (pt - job.pt0) * PT;             // first of the pair's boards
+    const int64_t s_warp = s_pair + wip * (2 * MT);         // first of this warp's boards
     // ---- inputs: 4 cells for each row tile (2 boards x 4 conv2 positions per tile) -------------------
     double x[MT][4];
 #pragma unroll
@@ -195,7 +233,7 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         a[mt] = relu(fma(x[mt][3], w.w, fma(x[mt][2], w.z, fma(x[mt][1], w.y, fma(x[mt][0], w.x, bias)))));
-        if (SAVE && s_warp + mt * 2 + (fr >> 2) < n)       // patch row 4*board + position = 4*s_warp + 8*mt + fr
+        if (save && s_warp + mt * 2 + (fr >> 2) < n)       // patch row 4*board + position = 4*s_warp + 8*mt + fr
           sv.patches2[(4 * s_warp + 8 * mt + fr) * 256 + c1 * 4 + fk] = a[mt];
       }
       const double* bf = w2f + c1 * 256 + lane;
@@ -225,8 +263,7 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
       }
     }
     pair_barrier(pair);
-    if (SAVE) {   // the pair's pooled rows are contiguous boards: 64 threads copy them out, coalesced
-      const int64_t s_pair = tile * TILE + pair * (4 * MT);
+    if (save) {   // the pair's pooled rows are contiguous boards: 64 threads copy them out, coalesced
       const int t64 = wip * 32 + lane;
       for (int i = t64; i < 4 * MT * 256; i += 64) {
         const int r = i >> 8, c = i & 255;
@@ -277,8 +314,8 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
     for (int nt = 0; nt < 4; ++nt) {
       const int hh = wip * 32 + nt * 8 + 2 * fk;
       const double v0 = relu(h[nt][0]), v1 = relu(h[nt][1]);
-      if (SAVE && fr < 4 * MT && tile * TILE + pair * (4 * MT) + fr < n)
-        *reinterpret_cast<double2*>(sv.act3 + (tile * TILE + pair * (4 * MT) + fr) * 64 + hh) = make_double2(v0, v1);
+      if (save && fr < 4 * MT && s_pair + fr < n)
+        *reinterpret_cast<double2*>(sv.act3 + (s_pair + fr) * 64 + hh) = make_double2(v0, v1);
 #pragma unroll
       for (int a = 0; a < 4; ++a) part[a] = fma(v1, w4s[a * 64 + hh + 1], fma(v0, w4s[a * 64 + hh], part[a]));
     }
@@ -291,7 +328,7 @@ __global__ void __launch_bounds__(64 * PAIRS, 1)
     if (wip == 1) qpartp[lane] = mine;
     pair_barrier(pair);
     if (wip == 0) {
-      const int64_t s = tile * TILE + pair * (4 * MT) + fr;   // pooled row fr of the pair (4 * MT valid rows)
+      const int64_t s = s_pair + fr;   // pooled row fr of the pair (4 * MT valid rows)
       if (fr < 4 * MT && s < n) q[4 * s + fk] = mine + qpartp[lane] + b4s[fk];
     }
     // Reuse across tiles is ordered by the barriers themselves: a warp stores into in2 for tile t+1 only
@@ -321,6 +358,33 @@ cudaError_t qnet_kernels_configure() {
 
 using namespace b2048;
 
+namespace {
+
+// one network, one job, `ctas` CTAs
+template <int MT, int PAIRS, bool SAVE>
+cudaError_t launch_single(const QJob& job, const QConvWeights& w, int scaling, int64_t sms, cudaStream_t st) {
+  constexpr int PT = 4 * MT;
+  QLaunch m{};
+  m.nnets = 1;
+  m.scaling = scaling;
+  m.job[0] = job;
+  m.job[0].pt0 = 0;
+  QNet& net = m.net[0];
+  net.w = w;
+  net.job0 = 0;
+  net.njobs = 1;
+  net.pts = (job.n + PT - 1) / PT;
+  const int64_t iters = (net.pts + PAIRS - 1) / PAIRS;          // CTA iterations if one CTA did everything
+  net.cta0 = 0;
+  net.ctas = (int)(iters < sms ? iters : sms);
+  net.per = ((iters + net.ctas - 1) / net.ctas) * PAIRS;         // whole iterations per CTA
+  net.ctas = (int)((net.pts + net.per - 1) / net.per);
+  qconv_forward_kernel<MT, PAIRS, SAVE><<<net.ctas, 64 * PAIRS, QS<PAIRS>::BYTES, st>>>(m);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
 extern "C" int qnet_conv_forward_f64(const uint64_t* boards, const double* states, int scaling, const double* w1,
                                      const double* b1, const double* w2, const double* b2, const double* w3,
                                      const double* b3, const double* w4, const double* b4, double* q, int64_t n,
@@ -341,14 +405,10 @@ extern "C" int qnet_conv_forward_f64(const uint64_t* boards, const double* state
   const int64_t c16 = 24 * ((t16 + sms - 1) / sms), c32 = 36 * ((t32 + sms - 1) / sms), c40 = 45 * ((t40 + sms - 1) / sms);
   const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c16 < c32 && c16 <= c40) {
-    qconv_forward_kernel<1, 4, false><<<(int)(t16 < sms ? t16 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n, QConvSaved{});
-  } else if (c40 < c32) {
-    qconv_forward_kernel<2, 5, false><<<(int)(t40 < sms ? t40 : sms), 320, QS<5>::BYTES, st>>>(boards, states, scaling, w, q, n, QConvSaved{});
-  } else {
-    qconv_forward_kernel<2, 4, false><<<(int)(t32 < sms ? t32 : sms), 256, QS<4>::BYTES, st>>>(boards, states, scaling, w, q, n, QConvSaved{});
-  }
-  return (int)cudaGetLastError();
+  const QJob job{boards, states, q, QConvSaved{nullptr, nullptr, nullptr}, n, 0};
+  if (c16 < c32 && c16 <= c40) return (int)launch_single<1, 4, false>(job, w, scaling, sms, st);
+  if (c40 < c32) return (int)launch_single<2, 5, false>(job, w, scaling, sms, st);
+  return (int)launch_single<2, 4, false>(job, w, scaling, sms, st);
 }
 
 extern "C" int qnet_conv_forward_train_f64(const double* states, const double* w1, const double* b1, const double* w2,
@@ -365,12 +425,66 @@ extern "C" int qnet_conv_forward_train_f64(const double* states, const double* w
   const int64_t t32 = (n + 31) / 32, t40 = (n + 39) / 40;
   const int64_t c32 = 36 * ((t32 + sms - 1) / sms), c40 = 45 * ((t40 + sms - 1) / sms);
   const QConvWeights w{w1, b1, w2, b2, w3, b3, w4, b4};
-  const QConvSaved sv{patches2, act2, act3};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c40 < c32) {
-    qconv_forward_kernel<2, 5, true><<<(int)(t40 < sms ? t40 : sms), 320, QS<5>::BYTES, st>>>(nullptr, states, 0, w, q, n, sv);
-  } else {
-    qconv_forward_kernel<2, 4, true><<<(int)(t32 < sms ? t32 : sms), 256, QS<4>::BYTES, st>>>(nullptr, states, 0, w, q, n, sv);
+  const QJob job{nullptr, states, q, QConvSaved{patches2, act2, act3}, n, 0};
+  if (c40 < c32) return (int)launch_single<2, 5, true>(job, w, 0, sms, st);
+  return (int)launch_single<2, 4, true>(job, w, 0, sms, st);
+}
+
+// The forwards of one Double-DQN update in ONE launch (src/dqn_lib.py:126-128 and :146): Q(s) of the online network with
+// the activations its backward pass needs, Q(s') of the online network (NULL: plain DQN) and Q(s') of the target
+// network.  The SMs are divided between the two weight sets in proportion to their boards and every CTA gets the
+// same number of boards (+-8): at batch 5000 that is 101 boards on each of 148 SMs instead of three launches of
+// 125 CTAs x 40 boards that queue behind each other.
+extern "C" int qnet_conv_forward_update_f64(const double* states, const double* next_states, const double* const* online,
+                                            const double* const* target, double* q, double* patches2, double* act2,
+                                            double* act3, double* q_next_online, double* q_next_target, int64_t n,
+                                            void* stream) {
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  if (n <= 0 || !states || !next_states || !online || !target || !q || !patches2 || !act2 || !act3 || !q_next_target)
+    return B2048_EINVAL;
+  for (int i = 0; i < 8; ++i)
+    if (!online[i] || !target[i]) return B2048_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(online[2]) | reinterpret_cast<uintptr_t>(target[2]) | reinterpret_cast<uintptr_t>(act3)) & 15u)
+    return B2048_EINVAL;
+  constexpr int MT = 2, PAIRS = 5, PT = 4 * MT;
+  const int64_t sms = ctx->sm_count;
+  const int64_t pts = (n + PT - 1) / PT;                       // pair tiles per batch
+  QLaunch m{};
+  m.nnets = 2;
+  m.scaling = 0;
+  const QConvSaved none{nullptr, nullptr, nullptr};
+  int nj = 0;
+  m.job[nj++] = QJob{nullptr, states, q, QConvSaved{patches2, act2, act3}, n, 0};
+  if (q_next_online) m.job[nj++] = QJob{nullptr, next_states, q_next_online, none, n, pts};
+  m.net[0].w = QConvWeights{online[0], online[1], online[2], online[3], online[4], online[5], online[6], online[7]};
+  m.net[0].job0 = 0;
+  m.net[0].njobs = nj;
+  m.net[0].pts = pts * nj;
+  m.job[nj] = QJob{nullptr, next_states, q_next_target, none, n, 0};
+  m.net[1].w = QConvWeights{target[0], target[1], target[2], target[3], target[4], target[5], target[6], target[7]};
+  m.net[1].job0 = nj;
+  m.net[1].njobs = 1;
+  m.net[1].pts = pts;
+  // CTAs per network in proportion to the pair tiles, at least one each, never more than one per CTA iteration
+  const int64_t total = m.net[0].pts + m.net[1].pts;
+  int64_t c1 = (sms * m.net[1].pts + total / 2) / total;
+  if (c1 < 1) c1 = 1;
+  if (c1 > sms - 1) c1 = sms - 1;
+  int64_t c0 = sms - c1;
+  int cta = 0;
+  int64_t want[2] = {c0, c1};
+  for (int i = 0; i < 2; ++i) {
+    QNet& net = m.net[i];
+    int64_t c = want[i] < net.pts ? want[i] : net.pts;
+    net.per = (net.pts + c - 1) / c;
+    c = (net.pts + net.per - 1) / net.per;
+    net.cta0 = cta;
+    net.ctas = (int)c;
+    cta += (int)c;
   }
+  qconv_forward_kernel<MT, PAIRS, true><<<cta, 64 * PAIRS, QS<PAIRS>::BYTES, static_cast<cudaStream_t>(stream)>>>(m);
   return (int)cudaGetLastError();
 }

@@ -10,6 +10,7 @@
 // shared-memory tiles, and a second small kernel adds the per-block partial sums in block order, so the
 // result is bit-reproducible (no atomics).
 #include "b2048_common.cuh"
+#include <cstdlib>
 
 namespace b2048 {
 namespace {
@@ -129,13 +130,17 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 
 __global__ void __launch_bounds__(256, 1)
     wgrad_dmma_kernel(const double* __restrict__ g, const double* __restrict__ x, double* __restrict__ partials,
-                      int64_t rows, int K) {
+                      int64_t rows, int K, int64_t rows_per_cta) {
   extern __shared__ __align__(16) double wsm[];
+  __shared__ double bsum[3][64];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
   const int O = 64 * K;
-  // CTA b takes row tiles b, b + grid, b + 2*grid, ...: a fixed assignment (the partial sums do not depend
-  // on scheduling) without a ragged tail per CTA
-  const int64_t r1 = rows, ntiles = (rows + WT_ROWS - 1) / WT_ROWS;
+  // CTA b owns the contiguous rows [b * rows_per_cta, ..) (a multiple of 4, the same for every CTA: the partial
+  // sums do not depend on scheduling) in tiles of 32; the last tile runs only the k-steps it has rows for, so a
+  // batch that is not a multiple of 32 * grid rows costs no CTA a whole extra tile (20 000 rows on 148 SMs:
+  // 136 rows each instead of 4 or 5 tiles of 32)
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
   const bool active = warp * 32 < K;
 
   auto stage = [&](int buf, int64_t t0) {     // rows [t0, t0+32) -> buffer `buf`; rows past r1 become zeros
@@ -160,13 +165,13 @@ __global__ void __launch_bounds__(256, 1)
   for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  double accb = 0.0;
+  double accb = 0.0;               // bias gradient: thread = (channel tid % 64, rows 8 * (tid / 64) .. + 7 of each tile)
 
   int buf = 0;
-  if (blockIdx.x < ntiles) stage(0, (int64_t)blockIdx.x * WT_ROWS);
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    if (tile + gridDim.x < ntiles) {
-      stage(buf ^ 1, (tile + gridDim.x) * WT_ROWS);
+  if (r0 < r1) stage(0, r0);
+  for (int64_t t0 = r0; t0 < r1; t0 += WT_ROWS) {
+    if (t0 + WT_ROWS < r1) {
+      stage(buf ^ 1, t0 + WT_ROWS);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -174,9 +179,10 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     const double* gs = wsm + buf * WT_BUF;
     const double* xs = gs + WT_ROWS * WT_GS;
+    const int ksteps = (int)(r1 - t0 < WT_ROWS ? (r1 - t0 + 3) / 4 : WT_ROWS / 4);
     if (active) {
 #pragma unroll 2
-      for (int ks = 0; ks < WT_ROWS / 4; ++ks) {
+      for (int ks = 0; ks < ksteps; ++ks) {
         // A[m = channel][k = row] = g[row][channel];  B[k = row][n = column] = x[row][column]
         const double* ga = gs + (ks * 4 + fk) * WT_GS + fr;
         const double* xb = xs + (ks * 4 + fk) * WT_XS + warp * 32 + fr;
@@ -194,9 +200,10 @@ __global__ void __launch_bounds__(256, 1)
         }
       }
     }
-    if (tid < 64) {
-#pragma unroll 8
-      for (int r = 0; r < WT_ROWS; ++r) accb += gs[r * WT_GS + tid];
+    {
+      const double* gb = gs + (tid >> 6) * 8 * WT_GS + (tid & 63);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) accb += gb[r * WT_GS];
     }
     __syncthreads();          // everyone is done with `buf` before the next iteration refills it
     buf ^= 1;
@@ -210,13 +217,24 @@ __global__ void __launch_bounds__(256, 1)
         *reinterpret_cast<double2*>(mine + (mt * 8 + fr) * K + warp * 32 + nt * 8 + 2 * fk) =
             make_double2(acc[mt][nt][0], acc[mt][nt][1]);
   }
-  if (tid < 64) mine[O + tid] = accb;
+  if (tid >= 64) bsum[(tid >> 6) - 1][tid & 63] = accb;
+  __syncthreads();
+  if (tid < 64) mine[O + tid] = ((accb + bsum[0][tid]) + bsum[1][tid]) + bsum[2][tid];
 }
 
-int64_t wt_blocks(int64_t rows, int sms) {
+// rows per CTA (a multiple of 4) and number of CTAs of wgrad_dmma_kernel
+void wt_plan(int64_t rows, int sms, int64_t* rows_per_cta, int64_t* blocks) {
   int64_t b = (rows + WT_ROWS - 1) / WT_ROWS;
   if (b > sms) b = sms;
-  return b < 1 ? 1 : b;
+  if (b < 1) b = 1;
+  const int64_t per = ((rows + b - 1) / b + 3) / 4 * 4;
+  *rows_per_cta = per;
+  *blocks = (rows + per - 1) / per;
+}
+int64_t wt_blocks(int64_t rows, int sms) {
+  int64_t per, b;
+  wt_plan(rows, sms, &per, &b);
+  return b;
 }
 
 // ---- first convolution of the conv Q-network: col2im + ReLU mask + weight / bias gradient in one pass ----
@@ -298,6 +316,226 @@ int64_t c1_blocks(int64_t n, int sms) {
   return b < 1 ? 1 : b;
 }
 
+// ---- second convolution's input gradient fused with the first convolution's whole backward ------------------
+// gp2 = g2 W2 ([4n,64] x [64,256], g2 = d loss / d conv2 pre-activation in (board, position) x channel rows)
+// is the gradient of the patch matrix; all that is ever done with it is the pass of conv1_wgrad_fused_kernel
+// above.  Materialised it is 2 x 41 MB of traffic at batch 5000 and two kernels on the critical path of the
+// update (28 + 48 us).  Here the product stays in the DMMA accumulators:
+//   * W2 sits in shared memory in B-fragment order for the whole launch (128 KB); every CTA stages ALL the g2
+//     rows it will ever need (<= 18 row tiles of 8 = 77 KB) in the prologue, so the eight warps run without a
+//     single CTA-wide barrier afterwards and drift apart: one warp's epilogue hides behind the others' DMMAs;
+//   * warp w owns patch columns [32w, 32w+32) = conv1 channels 8w .. 8w+7 (x 4 taps) for every row: a lane's two
+//     accumulator columns are the taps (ky, 0) and (ky, 1) of ONE channel, its row is one (board, position), so
+//     the ReLU mask is one 16-byte load of patches2 and dW1[c][.] / db1[c] accumulate against six board cells:
+//         dW1[c][t] += sum_tap mask * gp2[(b,pos), (c,tap)] * x[b, pos + tap + t]
+//     (col2im never happens: summing over (pos, tap) pairs that hit the same conv1 output commutes with the mask,
+//     which depends on that output only);
+//   * per-CTA partial sums in the layout conv1_wgrad_fused_kernel writes; wgrad_reduce_kernel adds them in a
+//     fixed order (bit-reproducible).
+constexpr int CB_THREADS = 256;
+constexpr int CB_SA = 68;                                  // doubles per staged g2 row (= 4 mod 16: conflict-free A fragments)
+constexpr int CB_MAX_MT = 18;                              // row tiles (2 boards each) a CTA stages at once
+constexpr int CB_W2_ELEMS = 64 * 256;
+constexpr int CB_SMEM_BYTES = (CB_W2_ELEMS + CB_MAX_MT * 8 * CB_SA) * 8;
+
+// MODE 0: the fused conv backward above.  MODE 1: the same [rows,64] x [64,256] product with a masked store instead —
+// out = (g w) * (h > 0), optionally regrouped (column c * T + t of row i -> row i * T + t, column c): fc1's input
+// gradient of the conv Q-network, whose reduction (64) is too short for K8's pipelined tiles to pay off
+// (dgemm_dmma_kernel: 23 us, a fifth of it DMMA).
+struct CbArgs {
+  const double* g;        // [rows, 64]
+  const double* w;        // [64, 256]
+  const double* h;        // [rows, 256]: patches2 (MODE 0) / the layer below's output (MODE 1)
+  const double* x;        // MODE 0: states [rows / 4, 16]
+  double* out;            // MODE 0: per-CTA partial records [grid][320];  MODE 1: the product
+  int64_t rows;
+  int chunk_mt;
+  int64_t nchunks;
+  int group;              // MODE 1: 0 = plain [rows, 256], T = regrouped [rows * T, 256 / T]
+  int stagger;            // cycles by which warps 4..7 start behind warps 0..3 (0 = together)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(CB_THREADS, 1) cb_kernel(const CbArgs p) {
+  extern __shared__ __align__(16) double cbsm[];
+  double* w2f = cbsm;                      // [16 k-steps][32 n-tiles][32 lanes]
+  double* g2s = cbsm + CB_W2_ELEMS;        // [chunk_mt * 8 rows][CB_SA]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+  const int64_t rows = p.rows;
+  const int chunk_mt = p.chunk_mt;
+
+  // B fragment of mma.m8n8k4 (col): lane holds B[k = lane % 4][n = lane / 4]; k-step ks covers reduction indices
+  // 4 ks .. 4 ks + 3, n-tile nt output columns 8 nt .. 8 nt + 7:  w2f[(ks*32 + nt)*32 + lane] = W[4 ks + lane%4][8 nt + lane/4]
+  for (int u = warp; u < 16 * 32; u += CB_THREADS / 32) {
+    const int ks = u >> 5, nt = u & 31;
+    const double* src = p.w + (ks * 4 + fk) * 256 + nt * 8 + fr;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w2f + u * 32 + lane);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  }
+
+  // MODE 0 — this lane's place in the fragments: row = (board, conv2 position pos), columns = taps (ky, 0), (ky, 1) of a channel
+  const int pos = fr & 3, ky = fk & 1;
+  const int cell0 = ((pos >> 1) + ky) * 4 + (pos & 1);      // board cell under tap (ky, 0) of position pos
+  double dw[4][4], db[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    db[nt] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dw[nt][t] = 0.0;
+  }
+
+  for (int64_t chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
+    const int64_t row0 = chunk * chunk_mt * 8;
+    if (chunk != (int64_t)blockIdx.x) __syncthreads();      // everyone is done with the previous chunk's rows
+    for (int i = tid; i < chunk_mt * 8 * 16; i += CB_THREADS) {   // 32-byte units, 16 per row; rows past the batch are zero-filled
+      const int r = i >> 4, c = (i & 15) * 4;
+      const bool ok = row0 + r < rows;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(g2s + r * CB_SA + c);
+      const double* src = ok ? p.g + (row0 + r) * 64 + c : p.g;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16), "l"(src + 2), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // Each scheduler hosts warps w and w + 4.  Left alone they run load issue, products and epilogue in lockstep;
+    // starting the upper four half a product loop later lets one warp's DMMA stream cover the other's epilogue.
+    if (p.stagger > 0 && warp >= 4 && chunk == (int64_t)blockIdx.x) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger) {}
+    }
+
+    for (int mt0 = 0; mt0 < chunk_mt; mt0 += 2) {
+      // ---- what the epilogue needs, requested before the products: ReLU masks (the forward values) and board cells
+      double2 act[2][4];
+      double xc[2][6];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int64_t row = row0 + (mt0 + mt) * 8 + fr;
+        const bool ok = mt0 + mt < chunk_mt && row < rows;
+        const double* pr = p.h + row * 256 + warp * 32 + 2 * fk;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) act[mt][nt] = ok ? __ldg(reinterpret_cast<const double2*>(pr + nt * 8)) : make_double2(0.0, 0.0);
+        if (MODE == 0) {
+          const double* xr = p.x + (row >> 2) * 16 + cell0;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) xc[mt][dy * 3 + dx] = ok ? __ldg(xr + dy * 4 + dx) : 0.0;
+        }
+      }
+      // ---- product tile: 16 rows x 32 columns per warp, reduction over 64 -------------------------------------
+      double acc[2][4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+      const double* ap = g2s + (mt0 * 8 + fr) * CB_SA + fk;
+      const double* bp = w2f + (warp * 4) * 32 + lane;
+#pragma unroll 4
+      for (int ks = 0; ks < 16; ++ks) {
+        double b[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[nt] = bp[(ks * 32 + nt) * 32];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const double a = ap[mt * 8 * CB_SA + ks * 4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
+                         : "d"(a), "d"(b[nt]));
+        }
+      }
+      // (the empty asm pins the compares behind the products: ptxas otherwise hoists them — and with them the wait
+      // for the mask loads — in front of the DMMA loop to save registers)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) asm volatile("" : "+d"(act[mt][nt].x), "+d"(act[mt][nt].y));
+      if (MODE == 0) {
+        // ---- mask, then accumulate against the cells: tap (ky, e) of weight tap t = (ty, tx) reads cell (ty, e + tx)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const double s0 = act[mt][nt].x > 0.0 ? acc[mt][nt][0] : 0.0;
+            const double s1 = act[mt][nt].y > 0.0 ? acc[mt][nt][1] : 0.0;
+            db[nt] += s0 + s1;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int o = (t >> 1) * 3 + (t & 1);
+              dw[nt][t] = fma(s1, xc[mt][o + 1], fma(s0, xc[mt][o], dw[nt][t]));
+            }
+          }
+      } else {
+        // ---- masked store; regrouped: columns j, j + 1 (j even, T even) share c = j / T and land in rows i*T + t, + 1
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int64_t row = row0 + (mt0 + mt) * 8 + fr;
+          if (mt0 + mt >= chunk_mt || row >= rows) continue;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int j = warp * 32 + nt * 8 + 2 * fk;
+            const double v0 = act[mt][nt].x > 0.0 ? acc[mt][nt][0] : 0.0;
+            const double v1 = act[mt][nt].y > 0.0 ? acc[mt][nt][1] : 0.0;
+            if (p.group) {
+              const int wd = 256 / p.group;
+              double* o = p.out + (row * p.group + j % p.group) * wd + j / p.group;
+              o[0] = v0;
+              o[wd] = v1;
+            } else {
+              *reinterpret_cast<double2*>(p.out + row * 256 + j) = make_double2(v0, v1);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (MODE != 0) return;
+
+  // ---- per-CTA record [64 channels x 4 taps | 64 bias]: sum over the 8 rows x 2 tap rows that share a channel ----
+  double* mine = p.out + (int64_t)blockIdx.x * 320;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    double v[5] = {dw[nt][0], dw[nt][1], dw[nt][2], dw[nt][3], db[nt]};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      v[j] += __shfl_xor_sync(0xFFFFFFFFu, v[j], 1);
+      v[j] += __shfl_xor_sync(0xFFFFFFFFu, v[j], 4);
+      v[j] += __shfl_xor_sync(0xFFFFFFFFu, v[j], 8);
+      v[j] += __shfl_xor_sync(0xFFFFFFFFu, v[j], 16);
+    }
+    if (fr == 0 && (fk & 1) == 0) {
+      const int c = warp * 8 + nt * 2 + (fk >> 1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) mine[c * 4 + t] = v[t];
+      mine[256 + c] = v[4];
+    }
+  }
+}
+
+int cb_stagger() {
+  static const int v = [] {
+    const char* e = getenv("B2048_CB_STAGGER");
+    return e ? atoi(e) : 2000;
+  }();
+  return v;
+}
+
+// chunking of cb_kernel: row tiles per chunk (even, <= CB_MAX_MT) and number of chunks, so that one round
+// of chunks covers the batch when it fits (5 000 boards: 2 500 row tiles = 139 chunks of 18)
+void cb_plan(int64_t rows, int sms, int* chunk_mt, int64_t* nchunks) {
+  const int64_t mtiles = (rows + 7) / 8;
+  const int64_t rounds = (mtiles + (int64_t)sms * CB_MAX_MT - 1) / ((int64_t)sms * CB_MAX_MT);
+  int64_t per = (mtiles + sms * rounds - 1) / (sms * rounds);
+  per = (per + 1) / 2 * 2;
+  if (per > CB_MAX_MT) per = CB_MAX_MT;
+  if (per < 2) per = 2;
+  *chunk_mt = (int)per;
+  *nchunks = (mtiles + per - 1) / per;
+}
+
 }  // namespace
 }  // namespace b2048
 
@@ -346,9 +584,10 @@ extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, d
   int err = 0;
   DeviceCtx* ctx = current_ctx(&err);
   if (!ctx) return err;
-  const int64_t blocks = wt_blocks(rows, ctx->sm_count);
+  int64_t blocks, rows_per_cta;
+  wt_plan(rows, ctx->sm_count, &rows_per_cta, &blocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K);
+  wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K, rows_per_cta);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int O = 64 * K;
@@ -358,7 +597,11 @@ extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, d
 
 namespace b2048 {
 cudaError_t wgrad_kernels_configure() {
-  return cudaFuncSetAttribute(wgrad_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(wgrad_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(cb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(cb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM_BYTES);
 }
 }  // namespace b2048
 
@@ -386,3 +629,52 @@ extern "C" int conv1_wgrad_fused_f64(const double* gpatches2, const double* patc
   wgrad_reduce_kernel<<<(320 + 31) / 32, 256, 0, st>>>(scratch, dw1, db1, 256, 64, (int)blocks);
   return (int)cudaGetLastError();
 }
+
+extern "C" int64_t conv2_dgrad_conv1_wgrad_scratch_elems(int64_t n) {
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx || n <= 0) return 0;
+  int chunk_mt;
+  int64_t nchunks;
+  cb_plan(4 * n, ctx->sm_count, &chunk_mt, &nchunks);
+  return (nchunks < ctx->sm_count ? nchunks : (int64_t)ctx->sm_count) * 320;
+}
+
+extern "C" int conv2_dgrad_conv1_wgrad_f64(const double* g2, const double* w2, const double* patches2, const double* states,
+                                           double* dw1, double* db1, double* scratch, int64_t n, void* stream) {
+  if (n <= 0 || !g2 || !w2 || !patches2 || !states || !dw1 || !db1 || !scratch ||
+      ((reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(patches2)) & 15u))
+    return B2048_EINVAL;
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  int chunk_mt;
+  int64_t nchunks;
+  cb_plan(4 * n, ctx->sm_count, &chunk_mt, &nchunks);
+  const int64_t blocks = nchunks < ctx->sm_count ? nchunks : (int64_t)ctx->sm_count;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const CbArgs p{g2, w2, patches2, states, scratch, 4 * n, chunk_mt, nchunks, 0, cb_stagger()};
+  cb_kernel<0><<<(unsigned)blocks, CB_THREADS, CB_SMEM_BYTES, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  wgrad_reduce_kernel<<<(320 + 31) / 32, 256, 0, st>>>(scratch, dw1, db1, 256, 64, (int)blocks);
+  return (int)cudaGetLastError();
+}
+
+// out = (g[rows,64] w[64,256]) * (h[rows,256] > 0), regrouped when group > 0 (see dense_linear_dgrad_regroup_f64):
+// the short-reduction input gradient on the weights-in-shared-memory kernel (MODE 1 of cb_kernel).
+namespace b2048 {
+int dgrad64x256_masked(const double* g, const double* w, const double* h, double* out, int64_t rows, int group,
+                       cudaStream_t st) {
+  int err = 0;
+  DeviceCtx* ctx = current_ctx(&err);
+  if (!ctx) return err;
+  int chunk_mt;
+  int64_t nchunks;
+  cb_plan(rows, ctx->sm_count, &chunk_mt, &nchunks);
+  const int64_t blocks = nchunks < ctx->sm_count ? nchunks : (int64_t)ctx->sm_count;
+  const CbArgs p{g, w, h, nullptr, out, rows, chunk_mt, nchunks, group, cb_stagger()};
+  cb_kernel<1><<<(unsigned)blocks, CB_THREADS, CB_SMEM_BYTES, st>>>(p);
+  return (int)cudaGetLastError();
+}
+}  // namespace b2048

@@ -350,6 +350,120 @@ def test_fused_conv1_backward_kernel(cuda, n):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 17, 300, 5000, 6001, 11000])
+def test_conv2_dgrad_conv1_backward_in_the_accumulators(cuda, n):
+    """conv2_dgrad_conv1_wgrad_f64 (patch-matrix gradient consumed inside the tensor-core accumulators) against
+    the unfused pair it replaces — dense_linear_dgrad_f64 (plain g2 W2) then conv1_wgrad_fused_f64 — and against
+    torch; run-to-run bit-identical.  11000 boards = more than one round of chunks per CTA."""
+    from b2048 import _lib
+    from b2048.env import _ptr, _stream
+    _lib.init(torch.device(cuda).index or 0)
+    L = _lib.lib()
+    torch.manual_seed(n)
+    kw = dict(dtype=torch.float64, device=cuda)
+    x = torch.randint(0, 12, (n, 16), device=cuda).double()
+    w1, b1 = torch.randn(64, 4, **kw), torch.randn(64, **kw)
+    w2 = torch.randn(64, 64, 2, 2, **kw)
+    xi = x.view(n, 4, 4)
+    p1 = torch.stack([xi[:, y + ky, xx + kx] for y in range(3) for xx in range(3) for ky in range(2) for kx in range(2)], 1).view(n * 9, 4)
+    out1 = torch.relu(p1 @ w1.t() + b1).view(n, 3, 3, 64)
+    p2 = torch.stack([out1[:, oy + ky, ox + kx, :] for oy in range(2) for ox in range(2) for ky in range(2) for kx in range(2)], 1)
+    p2 = p2.view(n, 4, 4, 64).permute(0, 1, 3, 2).reshape(4 * n, 256).contiguous()
+    g2 = torch.randn(4 * n, 64, **kw)
+    gp2 = g2 @ w2.view(64, 256)
+    g1 = torch.zeros(n, 3, 3, 64, **kw)
+    gv = gp2.view(n, 2, 2, 64, 2, 2)
+    for oy in range(2):
+        for ox in range(2):
+            for ky in range(2):
+                for kx in range(2):
+                    g1[:, oy + ky, ox + kx, :] += gv[:, oy, ox, :, ky, kx]
+    g1 = (g1 * (out1 > 0)).view(9 * n, 64)
+    want_w, want_b = g1.t() @ p1, g1.sum(0)
+    scratch = torch.empty(L.conv2_dgrad_conv1_wgrad_scratch_elems(n), **kw)
+    assert scratch.numel() > 0
+
+    def run():
+        dw, db = torch.full((64, 4), float("nan"), **kw), torch.full((64,), float("nan"), **kw)
+        with torch.cuda.device(cuda):
+            assert L.conv2_dgrad_conv1_wgrad_f64(_ptr(g2), _ptr(w2), _ptr(p2), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), n,
+                                                 _stream(x)) == 0
+        return dw, db
+
+    dw, db = run()
+    dw2, db2 = run()
+    tol_w = 1e-11 * max(1.0, float(want_w.abs().max()))
+    tol_b = 1e-11 * max(1.0, float(want_b.abs().max()))
+    assert float((dw - want_w).abs().max()) <= tol_w and float((db - want_b).abs().max()) <= tol_b
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    # the unfused kernels it replaces
+    gp2k = torch.empty(4 * n, 256, **kw)
+    s1 = torch.empty(L.conv1_wgrad_fused_scratch_elems(n), **kw)
+    dwu, dbu = torch.empty(64, 4, **kw), torch.empty(64, **kw)
+    with torch.cuda.device(cuda):
+        assert L.dense_linear_dgrad_f64(_ptr(g2), _ptr(w2), None, _ptr(gp2k), 4 * n, 256, 64, _stream(x)) == 0
+        assert L.conv1_wgrad_fused_f64(_ptr(gp2k), _ptr(p2), _ptr(x), _ptr(dwu), _ptr(dbu), _ptr(s1), n, _stream(x)) == 0
+    assert float((dw - dwu).abs().max()) <= tol_w and float((db - dbu).abs().max()) <= tol_b
+    with torch.cuda.device(cuda):
+        assert L.conv2_dgrad_conv1_wgrad_f64(_ptr(g2), _ptr(w2), _ptr(p2), _ptr(x), _ptr(dw), _ptr(db), _ptr(scratch), 0,
+                                             _stream(x)) == -2
+
+
+@pytest.mark.parametrize("n,double", [(1, True), (7, True), (8, False), (333, True), (5000, True), (5000, False), (20011, True)])
+def test_update_forwards_in_one_launch_are_bit_identical(cuda, n, double):
+    """qnet_conv_forward_update_f64 — Q(s) with saved activations, Q_online(s') and Q_target(s') as ONE K6
+    launch over two weight sets — gives exactly the tensors of the three separate launches
+    (qnet_conv_forward_train_f64 + 2 x qnet_conv_forward_f64), for ragged sizes and without the online Q(s')."""
+    import copy
+    from b2048 import qfused
+    from bench import conv_qnet
+    torch.manual_seed(n)
+    net = conv_qnet().to(cuda)
+    tgt = copy.deepcopy(net)
+    with torch.no_grad():
+        for p in tgt.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    on, tg = qfused.TrainableConvQ(net), qfused.TrainableConvQ(tgt)
+    x = torch.randint(0, 12, (n, 16), device=cuda).double()
+    xn = torch.randint(0, 12, (n, 16), device=cuda).double()
+    q, saved, qno, qnt = on.forward_update(x, xn, tg, use_double=double)
+    q1, saved1 = on.forward_saving(x)
+    assert torch.equal(q, q1)
+    for a, b in zip(saved, saved1):
+        assert torch.equal(a, b)
+    assert torch.equal(qnt, qfused.FusedConvQ(tgt)(xn))
+    if double:
+        assert torch.equal(qno, qfused.FusedConvQ(net)(xn))
+    else:
+        assert qno is None
+    want = tgt(xn.view(n, 1, 4, 4))
+    assert float((qnt - want).abs().max()) <= 1e-12 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("rows", [1, 37, 5000])
+def test_dgrad_regrouped_store_equals_dgrad_then_transpose(cuda, rows):
+    """dense_linear_dgrad_regroup_f64(group=4) writes (g W) * (h > 0) of the layer behind nn.Flatten as rows
+    (board, position) x channel: bit-identical to dense_linear_dgrad_f64 followed by the view/transpose/reshape
+    the conv backward used to do with an ATen copy."""
+    from b2048 import _lib
+    from b2048.env import _ptr, _stream
+    _lib.init(torch.device(cuda).index or 0)
+    L = _lib.lib()
+    torch.manual_seed(rows)
+    kw = dict(dtype=torch.float64, device=cuda)
+    g, w = torch.randn(rows, 64, **kw), torch.randn(64, 256, **kw)
+    h = torch.relu(torch.randn(rows, 256, **kw))
+    plain, re = torch.empty(rows, 256, **kw), torch.full((4 * rows, 64), float("nan"), **kw)
+    with torch.cuda.device(cuda):
+        assert L.dense_linear_dgrad_f64(_ptr(g), _ptr(w), _ptr(h), _ptr(plain), rows, 256, 64, _stream(g)) == 0
+        assert L.dense_linear_dgrad_regroup_f64(_ptr(g), _ptr(w), _ptr(h), _ptr(re), rows, 256, 64, 4, _stream(g)) == 0
+        assert L.dense_linear_dgrad_regroup_f64(_ptr(g), _ptr(w), _ptr(h), _ptr(re), rows, 256, 64, 3, _stream(g)) == -2
+        assert L.dense_linear_dgrad_regroup_f64(_ptr(g), _ptr(w), None, _ptr(re), rows, 256, 64, 4, _stream(g)) == -2
+    assert torch.equal(re, plain.view(rows, 64, 4).transpose(1, 2).reshape(4 * rows, 64))
+    want = (g @ w) * (h > 0)
+    assert float((plain - want).abs().max()) <= 1e-12 * max(1.0, float(want.abs().max()))
+
+
 def test_batched_player_baselines(cuda):
     """The reference's player.py policies at scale: random-legal and up-left baselines."""
     from b2048.player import BatchedPlayer
