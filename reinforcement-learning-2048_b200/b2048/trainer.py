@@ -102,6 +102,10 @@ class DDQNUpdater:
             # buffer (overwrite: no zeroing, no per-parameter accumulate kernels)
             loss, _, _, grad_q = ddqn.ddqn_target_loss(q_next_online, q_next_target, q_cur, actions, rewards, dones,
                                                        self.gamma, self.use_double, want_grad=True)
+            # the loss leaves for its reporting slot next to the backward pass, not behind Adam
+            self.side2.wait_stream(main)
+            with torch.cuda.stream(self.side2):
+                self.loss.copy_(loss.detach().reshape(()))
             self.f_model.backward_into(saved, grad_q, [p.grad for p in self.grads.params])
         else:
             loss, _, _ = ddqn.ddqn_loss(q_cur, q_next_online, q_next_target, actions, rewards, dones, self.gamma,
@@ -113,7 +117,10 @@ class DDQNUpdater:
         else:
             self.grads.allreduce_()
             self.opt.step()
-        self.loss.copy_(loss.detach().reshape(()))
+        if direct:
+            main.wait_stream(self.side2)
+        else:
+            self.loss.copy_(loss.detach().reshape(()))
 
     def update(self) -> torch.Tensor:
         """One update; returns the (device) loss tensor of this rank's batch."""

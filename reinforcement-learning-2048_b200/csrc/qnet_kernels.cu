@@ -21,6 +21,7 @@
 // DFMA/DADD/DSETP share the FP64 pipe with DMMA, so biases are folded into the accumulator
 // initialisation and ReLU is done with integer instructions.
 #include "b2048_common.cuh"
+#include <cstdlib>
 
 namespace b2048 {
 namespace {
@@ -88,8 +89,9 @@ struct QConvSaved {
 };
 // One launch = up to two networks (weight sets), each with its own CTAs, each evaluating up to two batches
 // ("jobs").  The unit of work is a PAIR TILE: the 4 * MT boards one warp pair carries through the network.  A
-// network's jobs are laid end to end in pair tiles; its CTAs split that range into equal contiguous pieces, and
-// within a CTA pair p takes tiles lo + p, lo + p + PAIRS, ...  A plain forward is one network with one job; the
+// network's jobs are laid end to end in pair tiles and dealt out to its (CTA, pair) slots round-robin with the CTA
+// index running fastest — tile t goes to pair (t / ctas) % PAIRS of CTA t % ctas — so every CTA gets the same number
+// of tiles (+-1) and the same mix of jobs.  A plain forward is one network with one job; the
 // Double-DQN update (src/dqn_lib.py:126-128, :146) is {online: Q(s) saving, Q(s')} + {target: Q(s')} in one
 // launch: 15 000 boards spread evenly over all SMs instead of three 125-CTA launches that run one after the other.
 struct QJob {
@@ -104,12 +106,13 @@ struct QNet {
   QConvWeights w;
   int cta0, ctas;           // this network's CTAs: [cta0, cta0 + ctas)
   int job0, njobs;          // its jobs: job[job0 .. job0 + njobs)
-  int64_t pts, per;         // pair tiles in total / per CTA
+  int64_t pts;              // pair tiles in total
 };
 struct QLaunch {
   QNet net[2];
   QJob job[4];
   int nnets, scaling;
+  int stagger;              // cycles by which pairs 2, 3 start behind pairs 0, 1 (0 = together)
 };
 template <int MT, int PAIRS, bool SAVE>
 __global__ void __launch_bounds__(64 * PAIRS, 1) qconv_forward_kernel(const QLaunch m) {
@@ -166,18 +169,17 @@ __global__ void __launch_bounds__(64 * PAIRS, 1) qconv_forward_kernel(const QLau
   double* qpartp = qpart + pair * 32;
 
   constexpr int PT = 4 * MT;                           // boards per pair tile, 2 * MT per warp
-  const int64_t pt_lo = (int64_t)((int)blockIdx.x - net.cta0) * net.per;
-  const int64_t pt_hi = pt_lo + net.per < net.pts ? pt_lo + net.per : net.pts;
+  const int64_t pt_step = (int64_t)net.ctas * PAIRS;
 #if QC_STAGGER
   // Each scheduler hosts one warp of pairs 0/1 and one of pairs 2/3.  Left alone they run conv2 (DMMA
   // bound) and epilogue + fc1 (latency bound) in lockstep; starting pairs 2/3 a third of a tile later
   // lets one warp's DMMA stream cover the other's epilogue.  Only worth it for long launches.
-  if (PAIRS == 4 && pair >= 2 && net.per >= 8 * PAIRS) {
+  if (PAIRS == 4 && pair >= 2 && m.stagger > 0) {
     const long long t0 = clock64();
-    while (clock64() - t0 < QC_STAGGER) {}
+    while (clock64() - t0 < m.stagger) {}
   }
 #endif
-  for (int64_t pt = pt_lo + pair; pt < pt_hi; pt += PAIRS) {
+  for (int64_t pt = (int64_t)pair * net.ctas + ((int)blockIdx.x - net.cta0); pt < net.pts; pt += pt_step) {
     // the job this pair tile belongs to (at most two per network) and the tile's first board in it
     const int ji = net.job0 + ((net.njobs > 1 && pt >= m.job[net.job0 + 1].pt0) ? 1 : 0);
     const QJob& job = m.job[ji];
@@ -360,6 +362,13 @@ using namespace b2048;
 
 namespace {
 
+// stagger (cycles) for a launch whose pairs run `rounds` tiles each
+int stagger_for(int64_t rounds) {
+  static const int min_rounds = [] { const char* e = getenv("B2048_QC_STAGGER_MIN"); return e ? atoi(e) : 3; }();
+  static const int cycles = [] { const char* e = getenv("B2048_QC_STAGGER"); return e ? atoi(e) : QC_STAGGER; }();
+  return rounds >= min_rounds ? cycles : 0;
+}
+
 // one network, one job, `ctas` CTAs
 template <int MT, int PAIRS, bool SAVE>
 cudaError_t launch_single(const QJob& job, const QConvWeights& w, int scaling, int64_t sms, cudaStream_t st) {
@@ -377,8 +386,7 @@ cudaError_t launch_single(const QJob& job, const QConvWeights& w, int scaling, i
   const int64_t iters = (net.pts + PAIRS - 1) / PAIRS;          // CTA iterations if one CTA did everything
   net.cta0 = 0;
   net.ctas = (int)(iters < sms ? iters : sms);
-  net.per = ((iters + net.ctas - 1) / net.ctas) * PAIRS;         // whole iterations per CTA
-  net.ctas = (int)((net.pts + net.per - 1) / net.per);
+  m.stagger = stagger_for(net.pts / ((int64_t)net.ctas * PAIRS));
   qconv_forward_kernel<MT, PAIRS, SAVE><<<net.ctas, 64 * PAIRS, QS<PAIRS>::BYTES, st>>>(m);
   return cudaGetLastError();
 }
@@ -449,7 +457,8 @@ extern "C" int qnet_conv_forward_update_f64(const double* states, const double* 
     if (!online[i] || !target[i]) return B2048_EINVAL;
   if ((reinterpret_cast<uintptr_t>(online[2]) | reinterpret_cast<uintptr_t>(target[2]) | reinterpret_cast<uintptr_t>(act3)) & 15u)
     return B2048_EINVAL;
-  constexpr int MT = 2, PAIRS = 5, PT = 4 * MT;
+  // four warp pairs (two warps per scheduler): with five, two schedulers carry three warps and bound the launch
+  constexpr int MT = 2, PAIRS = 4, PT = 4 * MT;
   const int64_t sms = ctx->sm_count;
   const int64_t pts = (n + PT - 1) / PT;                       // pair tiles per batch
   QLaunch m{};
@@ -478,13 +487,13 @@ extern "C" int qnet_conv_forward_update_f64(const double* states, const double* 
   int64_t want[2] = {c0, c1};
   for (int i = 0; i < 2; ++i) {
     QNet& net = m.net[i];
-    int64_t c = want[i] < net.pts ? want[i] : net.pts;
-    net.per = (net.pts + c - 1) / c;
-    c = (net.pts + net.per - 1) / net.per;
+    const int64_t slots = (net.pts + PAIRS - 1) / PAIRS;
+    const int64_t c = want[i] < slots ? want[i] : slots;
     net.cta0 = cta;
     net.ctas = (int)c;
     cta += (int)c;
   }
+  m.stagger = stagger_for(total / ((int64_t)cta * PAIRS));
   qconv_forward_kernel<MT, PAIRS, true><<<cta, 64 * PAIRS, QS<PAIRS>::BYTES, static_cast<cudaStream_t>(stream)>>>(m);
   return (int)cudaGetLastError();
 }

@@ -432,20 +432,29 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cb_kernel(const CbArgs p) {
         for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
       const double* ap = g2s + (mt0 * 8 + fr) * CB_SA + fk;
       const double* bp = w2f + (warp * 4) * 32 + lane;
-#pragma unroll 4
+      // fragments of k-step ks + 1 are requested before the products of k-step ks are issued: a warp sits on its DMMAs
+      // (16 cycles of the pipe each), so loads issued after them would start a full k-step late
+      double a[2][2], b[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) b[0][nt] = bp[nt * 32];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) a[0][mt] = ap[mt * 8 * CB_SA];
+#pragma unroll
       for (int ks = 0; ks < 16; ++ks) {
-        double b[4];
+        const int cur = ks & 1, nxt = cur ^ 1;
+        if (ks + 1 < 16) {
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) b[nt] = bp[(ks * 32 + nt) * 32];
+          for (int nt = 0; nt < 4; ++nt) b[nxt][nt] = bp[((ks + 1) * 32 + nt) * 32];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const double a = ap[mt * 8 * CB_SA + ks * 4];
+          for (int mt = 0; mt < 2; ++mt) a[nxt][mt] = ap[mt * 8 * CB_SA + (ks + 1) * 4];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                          : "+d"(acc[mt][nt][0]), "+d"(acc[mt][nt][1])
-                         : "d"(a), "d"(b[nt]));
-        }
+                         : "d"(a[cur][mt]), "d"(b[cur][nt]));
       }
       // (the empty asm pins the compares behind the products: ptxas otherwise hoists them — and with them the wait
       // for the mask loads — in front of the DMMA loop to save registers)
