@@ -22,7 +22,10 @@ for rep in range(5):
     res.append(e0.elapsed_time(e1) / 20)
 res.sort()
 chk = int(out[0][:1 << 20].sum().item()) & 0xFFFFFFFF
-print(f"min {res[0]:.4f} med {res[2]:.4f} ms  ({n * 22 / res[0] / 1e6:.0f} GB/s)  chk {chk:08x}")
+m = 1 << 22
+w = torch.arange(1, m + 1, device=dev, dtype=torch.int64)
+chk2 = int(((out[2][:m].to(torch.int64) * w).sum() + (out[1][:m].to(torch.int64) * w).sum()).item()) & 0xFFFFFFFF
+print(f"min {res[0]:.4f} med {res[2]:.4f} ms  ({n * 22 / res[0] / 1e6:.0f} GB/s)  chk {chk:08x} flags+reward {chk2:08x}")
 '''
 def run(lib):
     envv = dict(os.environ)

@@ -59,11 +59,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // Per-board tail shared by the step kernels: spawn one tile iff the move changed the board.
 //   D   : the board's spawn draw (16-bit Philox lane in the upper half, see spawn_draw16)
 //   ovr : spawn override byte (B2048_SPAWN_NONE = none)
-template <bool HAS_OVERRIDE, class A = Add7>
+template <bool HAS_OVERRIDE, class A = Add7, bool DLOW = false>
 __device__ __forceinline__ void finish_board(uint32_t& nlo, uint32_t& nhi, uint32_t changed, uint32_t D,
                                              uint32_t p4, uint32_t ovr, uint32_t& flags, A add = A()) {
   if (!HAS_OVERRIDE || ovr == B2048_SPAWN_NONE) {
-    spawn_draw16(nlo, nhi, D, p4, changed, add);
+    spawn_draw16<A, DLOW>(nlo, nhi, D, p4, changed, add);
   } else if (changed && ovr != B2048_SPAWN_SKIP) {
     if (!spawn_at(nlo, nhi, ovr & 0xFu, (ovr >> 4) & 0xFu)) flags |= B2048_FLAG_BADSPAWN;
   }
@@ -81,16 +81,48 @@ constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 // table reads use explicit shared-space loads on a 32-bit base address computed once: with generic
 // pointers ptxas re-derived the shared window base (S2R + MOV + LEA) for every board.
 constexpr uint32_t SM_ACT = (uint32_t)LUT_SMEM_BYTES;   // 4 rows x 32 B: per-action transform constants
-constexpr uint32_t SM_LEGAL = SM_ACT + 128;             // 4 rows x 32 B: flags byte per (action, frame mask)
-constexpr uint32_t SM_CONST = SM_LEGAL + 128;           // run-time constants (StreamConsts)
+#ifndef B2048_V_FLAGIDP
+#define B2048_V_FLAGIDP 1   // 1: the RIGHT / OVERFLOW bits of the four table entries index the flags table through ONE IDP.4A
+#endif
+// flags byte per (action, frame mask): 4 rows x 32 B; with B2048_V_FLAGIDP 16 such blocks, one per combination of the
+// RIGHT / OVERFLOW bits of row pairs (0,1) and (2,3)
+constexpr uint32_t SM_LEGAL = SM_ACT + 128;
+constexpr uint32_t SM_LEGAL_BYTES = B2048_V_FLAGIDP ? 2048 : 128;
+constexpr uint32_t SM_CONST = SM_LEGAL + SM_LEGAL_BYTES;  // run-time constants (StreamConsts)
 constexpr uint32_t SM_BAR = SM_CONST + 32;              // mbarrier
-constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
+constexpr uint32_t SM_COLD = SM_BAR + 16;               // ColdArgs: the kernel arguments the cold path needs
+// Arguments of the cold path (fix_quad), parked in shared memory by thread 0: ptxas hoists the argument set-up of a
+// __noinline__ call above the (never taken) branch, which cost ten LDC per iteration when they were call arguments.
+struct ColdArgs {
+  const uint4* boards2;
+  const uint32_t* actions4;
+  uint4* next2;
+  uint4* reward4;
+  uint32_t* flags4;
+  const uint32_t* glut;
+  const uint32_t* override4;
+  uint64_t step, index_base;
+  PhiloxKeys keys;
+  uint32_t p4;
+};
+constexpr int STREAM_SMEM_BYTES = (int)(SM_COLD + ((sizeof(ColdArgs) + 15) & ~size_t(15)));
+static_assert(STREAM_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 
 // Instruction selection in stream_board follows measurements on B200 (profiles/ubench):
 // the integer ALU pipe (LOP3/SHF/PRMT/ISETP/SEL/VIMNMX) issues one warp instruction per 2 cycles and is
 // the busiest unit, the FMA pipe (IMAD, IDP) has room.  So table addresses and 16-bit extracts are
 // integer dot products (IDP.2A/4A: "half-word * 4 + base" in one FMA-pipe instruction, no PRMT/LEA),
 // the "+0x7777.." of the nibble tests is an IMAD through a run-time 1, and selectors go to PRMT raw.
+#ifndef B2048_V_CCONST
+#define B2048_V_CCONST 1   // 1: IDP weights of the per-board action offsets as constant-bank operands (no UMOV per board)
+#endif
+#if B2048_V_CCONST
+__constant__ uint32_t c_saw[4] = {0x20u, 0x2000u, 0x200000u, 0x20000000u};
+__constant__ uint32_t c_kw[4] = {0x04000004u, 0x01000000u, 0x0404u, 0x08000200u};
+#endif
+#ifndef B2048_V_DLOW
+#define B2048_V_DLOW 1
+#endif
 #ifndef B2048_V_REGCONST
 #define B2048_V_REGCONST 1   // 1: dot-product weights and p4 live in registers (read once from shared memory, opaque to ptxas)
 #endif
@@ -98,8 +130,23 @@ constexpr int STREAM_SMEM_BYTES = (int)SM_BAR + 16;
 // threshold too, so that ptxas does not re-materialise them (UMOV / LDC) for every board
 struct StreamConsts {
   uint32_t one, p4, k4, k16, k44;
+#if B2048_V_FLAGIDP == 2
+  uint32_t kfl;
+#endif
 };
-#if B2048_V_REGCONST
+#if B2048_V_FLAGIDP == 2
+#define K_WFL(k) (k).kfl
+#elif B2048_V_CCONST
+#define K_WFL(k) c_kw[3]
+#else
+#define K_WFL(k) 0x08000200u
+#endif
+#if B2048_V_CCONST == 2
+#define K_W4(k) c_kw[0]
+#define K_W16(k) c_kw[1]
+#define K_W44(k) c_kw[2]
+#define K_P4(k, p4) (k).p4
+#elif B2048_V_REGCONST
 #define K_W4(k) (k).k4
 #define K_W16(k) (k).k16
 #define K_W44(k) (k).k44
@@ -144,14 +191,26 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
   }
   if (threadIdx.x == 0) {
     uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
-    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4;
+    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4; k[5] = 0x08000200u;
   }
+#if B2048_V_FLAGIDP
+  // block = R01 + 2 * O01 + 4 * R23 + 8 * O23 (bits 14 / 15 of the entries' upper halves, times the IDP weights 2 and 8
+  // of bytes 1 and 3); inside a block: 32 * action + changed + 2 * up + 4 * down
+  for (uint32_t t = threadIdx.x; t < SM_LEGAL_BYTES; t += blockDim.x) {
+    const uint32_t blk = t >> 7, a = (t >> 5) & 3u, m = t & 31u;
+    const uint32_t right = (blk | (blk >> 2)) & 1u, ovf = ((blk >> 1) | (blk >> 3)) & 1u;
+    const uint32_t zm = (m & 1u) | (right << 1) | ((m & 6u) << 1);
+    smem_raw[SM_LEGAL + t] = (uint8_t)(zframe_to_legal((int)a, zm) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
+                                       (ovf ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
+  }
+#else
   if (threadIdx.x < 128) {
     const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
     smem_raw[SM_LEGAL + threadIdx.x] =
         (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
                   ((m & 16u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
   }
+#endif
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
@@ -174,7 +233,7 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
 // four boards lets ptxas overlap the shared-memory latency of one board with the arithmetic of the others.
 constexpr uint32_t LUT_LIM2 = ((uint32_t)LUT_SMEM_ROWS - 1u) * 0x00010001u;   // last staged row, both halves
 static_assert(LUT_SMEM_ROWS - 1 == 0xDFFF, "the clamp row must be one whose entry has the OVERFLOW bit");
-template <bool HAS_OVERRIDE>
+template <bool HAS_OVERRIDE, bool DLOW = false>
 __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa,
                                              uint32_t lo, uint32_t hi, uint32_t D, uint32_t p4, uint32_t ovr,
                                              uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags,
@@ -229,12 +288,19 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa,
   const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
 #endif
   // table index built on top of the row address with five predicated adds (no SEL, no final add)
+#if B2048_V_FLAGIDP
+  uint32_t fa = __dp4a(fl & 0xC000C000u, K_WFL(kc), sa);   // + 128 * (R01 + 2 O01 + 4 R23 + 8 O23)
+  if (changed) fa += 1u;
+  if (up) fa += 2u;
+  if (dn_l | (dn_h & 0x0000FFFFu)) fa += 4u;
+#else
   uint32_t fa = sa;
   if (changed) fa += 1u;
   if (fl & 0x40004000u) fa += 2u;
   if (up) fa += 4u;
   if (dn_l | (dn_h & 0x0000FFFFu)) fa += 8u;
   if (fl & 0x80008000u) fa += 16u;
+#endif
 #ifdef B2048_DIAG_NOFLAGS
   flags = changed ? 1u : 0u; (void)fa;
 #else
@@ -251,18 +317,104 @@ __device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa,
 #ifdef B2048_DIAG_NOSPAWN
   olo ^= changed ? D : 0u;
 #else
-  finish_board<HAS_OVERRIDE>(olo, ohi, changed, D, K_P4(kc, p4), ovr, flags, add);
+  finish_board<HAS_OVERRIDE, Add7Fma, DLOW>(olo, ohi, changed, D, K_P4(kc, p4), ovr, flags, add);
 #endif
 }
+
+#ifndef B2048_V_PAIRLEGAL
+#define B2048_V_PAIRLEGAL 1
+#endif
+#if B2048_V_PAIRLEGAL
+// ---- two boards at a time ------------------------------------------------------------------------------------
+// Same arithmetic as stream_board, split into three phases so that the perpendicular legality of TWO boards can
+// share one word: the vertical pairs (row 0, row 1) and (row 1, row 2) of a board fill its low word, the third pair
+// (row 2, row 3) only half of the high word -- the third pairs of boards A and B are packed into one word
+// ([row2_A, row2_B] against [row3_A, row3_B]): three words of nibble tests per two boards instead of four.
+struct BoardMid {
+  uint32_t zl, zh, olo, ohi, fa, changed;
+};
+__device__ __forceinline__ void board_slide(uint32_t sbase, uint32_t sa, uint32_t lo, uint32_t hi, BoardMid& m,
+                                            uint32_t& reward, const StreamConsts& kc) {
+  const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
+  const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
+  uint32_t zl = prmt_raw(lo, hi, xa.x);
+  uint32_t zh = prmt_raw(lo, hi, xa.y);
+  {
+    const uint32_t tl = (zl ^ (zl >> xb.y)) & xb.z, th = (zh ^ (zh >> xb.y)) & xb.z;
+    zl ^= tl ^ (tl * xb.x);
+    zh ^= th ^ (th * xb.x);
+  }
+  const uint32_t cl = __vminu2(zl, LUT_LIM2), ch = __vminu2(zh, LUT_LIM2);
+  const uint32_t sl = cl ^ ((cl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+  const uint32_t sh = ch ^ ((ch >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
+  const uint32_t e0 = lds32(__dp2a_lo(sl, K_W4(kc), sbase));
+  const uint32_t e1 = lds32(__dp2a_hi(sl, K_W4(kc), sbase));
+  const uint32_t e2 = lds32(__dp2a_lo(sh, K_W4(kc), sbase));
+  const uint32_t e3 = lds32(__dp2a_hi(sh, K_W4(kc), sbase));
+  uint32_t wl = __byte_perm(e0, e1, 0x5410);
+  uint32_t wh = __byte_perm(e2, e3, 0x5410);
+  const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
+  const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
+  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));
+  m.changed = (wl ^ zl) | (wh ^ zh);
+  m.fa = __dp4a((h01 | h23) & 0xC000C000u, K_WFL(kc), sa);   // + 128 * (R01 + 2 O01 + 4 R23 + 8 O23)
+  if (m.changed) m.fa += 1u;
+  m.zl = zl; m.zh = zh;
+  {  // back to the board's own frame (the spawn comes after the pair step)
+    const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
+    wl ^= tl ^ (tl * xb.x);
+    wh ^= th ^ (th * xb.x);
+  }
+  m.olo = prmt_raw(wl, wh, xa.z);
+  m.ohi = prmt_raw(wl, wh, xa.w);
+}
+// perpendicular legality of boards A and B in their transformed frames, added to their flag-table addresses
+__device__ __forceinline__ void pair_legal(BoardMid& a, BoardMid& b, const StreamConsts& kc) {
+  const Add7Fma add{kc.one};
+  const uint32_t P = __byte_perm(a.zh, b.zh, 0x5410), Q = __byte_perm(a.zh, b.zh, 0x7632);   // rows 2 / rows 3
+  const uint32_t nP = nz3(P, add), nQ = nz3(Q, add), neP = ne3_dirty(P, Q, add);
+  const uint32_t up3 = nQ & ~(nP & neP), dn3 = nP & ~(nQ & neP);
+  {
+    const uint32_t n = nz3(a.zl, add), v = __byte_perm(a.zl, a.zh, 0x5432), ne = ne3_dirty(a.zl, v, add);
+    const uint32_t nv = __byte_perm(n, nP, 0x5432);
+    if ((nv & ~(n & ne)) | (up3 & 0x0000FFFFu)) a.fa += 2u;
+    if ((n & ~(nv & ne)) | (dn3 & 0x0000FFFFu)) a.fa += 4u;
+  }
+  {
+    const uint32_t n = nz3(b.zl, add), v = __byte_perm(b.zl, b.zh, 0x5432), ne = ne3_dirty(b.zl, v, add);
+    const uint32_t nv = __byte_perm(n, nP, 0x7632);
+    if ((nv & ~(n & ne)) | (up3 & 0xFFFF0000u)) b.fa += 2u;
+    if ((n & ~(nv & ne)) | (dn3 & 0xFFFF0000u)) b.fa += 4u;
+  }
+}
+template <bool HAS_OVERRIDE, bool DLOW>
+__device__ __forceinline__ void board_finish(const BoardMid& m, uint32_t D,
+                                             uint32_t p4, uint32_t ovr, uint32_t& olo, uint32_t& ohi, uint32_t& flags,
+                                             const StreamConsts& kc) {
+  const Add7Fma add{kc.one};
+  flags = lds8(m.fa + SM_LEGAL);               // legal | DONE | CHANGED | OVERFLOW
+  olo = m.olo;
+  ohi = m.ohi;
+  finish_board<HAS_OVERRIDE, Add7Fma, DLOW>(olo, ohi, m.changed, D, K_P4(kc, p4), ovr, flags, add);
+}
+#endif
 
 // Cold path of the streaming kernel: recompute the four boards of one quad with the full table in
 // global memory (same arithmetic as step_small_kernel) and overwrite the quad's outputs.
 template <bool HAS_OVERRIDE>
-__device__ __noinline__ void fix_quad(uint32_t quad, const uint4* __restrict__ boards2,
-                                      const uint32_t* __restrict__ actions4, uint4* __restrict__ next2,
-                                      uint4* __restrict__ reward4, uint32_t* __restrict__ flags4,
-                                      const uint32_t* __restrict__ glut, const PhiloxKeys keys, uint64_t step,
-                                      uint64_t index_base, uint32_t p4, const uint32_t* __restrict__ override4) {
+__device__ __noinline__ void fix_quad(uint32_t quad) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ColdArgs& ca = *reinterpret_cast<const ColdArgs*>(smem_raw + SM_COLD);
+  const uint4* boards2 = ca.boards2;
+  const uint32_t* actions4 = ca.actions4;
+  uint4* next2 = ca.next2;
+  uint4* reward4 = ca.reward4;
+  uint32_t* flags4 = ca.flags4;
+  const uint32_t* glut = ca.glut;
+  const uint32_t* override4 = ca.override4;
+  const uint64_t step = ca.step, index_base = ca.index_base;
+  const PhiloxKeys& keys = ca.keys;
+  const uint32_t p4 = ca.p4;
   const uint64_t* bq = reinterpret_cast<const uint64_t*>(boards2) + 4ull * quad;
   uint64_t* nq = reinterpret_cast<uint64_t*>(next2) + 4ull * quad;
   int32_t* rq = reinterpret_cast<int32_t*>(reward4) + 4ull * quad;
@@ -296,31 +448,68 @@ __device__ __forceinline__ void ld_quad(bool pred, const uint4* boards2, const u
   }
 }
 
-// Four boards: slide + merge + flags + spawn, three coalesced stores.  Returns true when the quad has to
-// be redone on the cold path (a clamped or overflowing row raised B2048_FLAG_OVERFLOW).
+// Four boards: slide + merge + flags + spawn, three coalesced stores.  Returns the packed flags word: the quad has
+// to be redone on the cold path when a clamped or overflowing row raised B2048_FLAG_OVERFLOW in one of its bytes.
 template <bool HAS_OVERRIDE>
-__device__ __forceinline__ bool stream_quad(uint32_t sbase, const StreamConsts& one, uint32_t p4, const uint4& ba,
+__device__ __forceinline__ uint32_t stream_quad(uint32_t sbase, const StreamConsts& one, uint32_t p4, const uint4& ba,
                                             const uint4& bb, uint32_t a4, uint32_t o4, uint32_t w_lo, uint32_t w_hi,
                                             uint32_t quad, uint4* __restrict__ next2, uint4* __restrict__ reward4,
                                             uint32_t* __restrict__ flags4) {
   const uint32_t a32 = a4 & 0x03030303u;     // byte j * 32 + base = one IDP.4A per board
+#if B2048_V_CCONST
+#define SA_OF(j) __dp4a(a32, c_saw[j], sbase)
+#else
 #define SA_OF(j) __dp4a(a32, 0x20u << (8 * (j)), sbase)
+#endif
   uint32_t n0l, n0h, n1l, n1h, n2l, n2h, n3l, n3h, rw0, rw1, rw2, rw3, f, fw;
   // draws: 16-bit lanes of the octet's Philox words, moved to the upper half (low lane first);
   // the four flag bytes are packed as they arrive (one live register instead of four)
+  // (odd lanes hand their draw over in the low half: B2048_V_DLOW, see spawn_draw16)
+#if B2048_V_DLOW
+#define D_ODD(w) __dp2a_hi((w), K_W16(one), 0u)
+#else
+#define D_ODD(w) ((w) & 0xFFFF0000u)
+#endif
+#if B2048_V_PAIRLEGAL
+  static_assert(B2048_V_FLAGIDP == 1 && B2048_V_DLOW == 1, "the pair path assumes the current defaults");
+  {
+    BoardMid ma, mb;
+    const uint32_t sa0 = SA_OF(0), sa1 = SA_OF(1);
+    board_slide(sbase, sa0, ba.x, ba.y, ma, rw0, one);
+    board_slide(sbase, sa1, ba.z, ba.w, mb, rw1, one);
+    pair_legal(ma, mb, one);
+    board_finish<HAS_OVERRIDE, false>(ma, w_lo << 16, p4, o4 & 0xFFu, n0l, n0h, fw, one);
+    board_finish<HAS_OVERRIDE, true>(mb, D_ODD(w_lo), p4, (o4 >> 8) & 0xFFu, n1l, n1h, f, one);
+    fw += f * 256u;
+  }
+  {
+    BoardMid ma, mb;
+    const uint32_t sa2 = SA_OF(2), sa3 = SA_OF(3);
+    board_slide(sbase, sa2, bb.x, bb.y, ma, rw2, one);
+    board_slide(sbase, sa3, bb.z, bb.w, mb, rw3, one);
+    pair_legal(ma, mb, one);
+    board_finish<HAS_OVERRIDE, false>(ma, w_hi << 16, p4, (o4 >> 16) & 0xFFu, n2l, n2h, f, one);
+    fw += f * 65536u;
+    board_finish<HAS_OVERRIDE, true>(mb, D_ODD(w_hi), p4, o4 >> 24, n3l, n3h, f, one);
+    fw += f * 16777216u;
+  }
+#else
   stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), ba.x, ba.y, w_lo << 16, p4, o4 & 0xFFu, n0l, n0h, rw0, fw, one);
-  stream_board<HAS_OVERRIDE>(sbase, SA_OF(1), ba.z, ba.w, w_lo & 0xFFFF0000u, p4, (o4 >> 8) & 0xFFu, n1l, n1h, rw1,
-                             f, one);
+  stream_board<HAS_OVERRIDE, B2048_V_DLOW != 0>(sbase, SA_OF(1), ba.z, ba.w, D_ODD(w_lo), p4, (o4 >> 8) & 0xFFu, n1l, n1h,
+                                                rw1, f, one);
   fw += f * 256u;
   stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), bb.x, bb.y, w_hi << 16, p4, (o4 >> 16) & 0xFFu, n2l, n2h, rw2, f, one);
   fw += f * 65536u;
-  stream_board<HAS_OVERRIDE>(sbase, SA_OF(3), bb.z, bb.w, w_hi & 0xFFFF0000u, p4, o4 >> 24, n3l, n3h, rw3, f, one);
+  stream_board<HAS_OVERRIDE, B2048_V_DLOW != 0>(sbase, SA_OF(3), bb.z, bb.w, D_ODD(w_hi), p4, o4 >> 24, n3l, n3h, rw3, f,
+                                                one);
   fw += f * 16777216u;
+#endif
+#undef D_ODD
 #undef SA_OF
   st_stream_v8(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h), make_uint4(n2l, n2h, n3l, n3h));
   st_stream_v4(reward4 + quad, make_uint4(rw0, rw1, rw2, rw3));
   flags4[quad] = fw;
-  return (fw & (B2048_FLAG_OVERFLOW * 0x01010101u)) != 0u;
+  return fw;
 }
 
 // ---- streaming kernel: eight boards (two quads, one Philox call) per thread and iteration -------------
@@ -346,6 +535,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   // previous kernel's output waits at griddepcontrol.wait below.
   asm volatile("griddepcontrol.launch_dependents;");
 
+  if (threadIdx.x == 0) {
+    ColdArgs& ca = *reinterpret_cast<ColdArgs*>(smem_raw + SM_COLD);
+    ca.boards2 = boards2; ca.actions4 = actions4; ca.next2 = next2; ca.reward4 = reward4; ca.flags4 = flags4;
+    ca.glut = glut; ca.override4 = override4; ca.step = step; ca.index_base = index_base; ca.keys = keys; ca.p4 = p4;
+  }
   stage_tables(smem_raw, bar, glut, p4);
 
   // 32-bit octet / quad indices (the host wrapper keeps nocts < 2^31): every global address is then one
@@ -370,8 +564,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     const uint4 k = lds128(sbase + SM_CONST);
     one.one = k.y; one.k4 = k.x; one.k16 = k.z; one.k44 = k.w;
     one.p4 = lds32(sbase + SM_CONST + 16);
+#if B2048_V_FLAGIDP == 2
+    one.kfl = lds32(sbase + SM_CONST + 20);
+#endif
   }
 
+  constexpr uint32_t OVF4 = B2048_FLAG_OVERFLOW * 0x01010101u;
   while (oct < no) {
     ld_quad(true, boards2, actions4, override4, HAS_OVERRIDE, 2u * oct + 1u, ya, yb, ay, oy);
 
@@ -398,17 +596,20 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                      __funnelshift_r(c3, c4, sh));
     }
 
-    if (__builtin_expect(stream_quad<HAS_OVERRIDE>(sbase, one, p4, xa, xb, ax, ox, w.x, w.y, 2u * oct, next2, reward4,
-                                                   flags4), 0))
-      fix_quad<HAS_OVERRIDE>(2u * oct, boards2, actions4, next2, reward4, flags4, glut, keys, step, index_base, p4,
-                             override4);
+    // (one merged test per octet was slower: 0.2976 vs 0.2941 ms)
+    if (__builtin_expect((stream_quad<HAS_OVERRIDE>(sbase, one, p4, xa, xb, ax, ox, w.x, w.y, 2u * oct, next2, reward4,
+                                                    flags4) & OVF4) != 0u, 0))
+      fix_quad<HAS_OVERRIDE>(2u * oct);
     // refill X for this thread's next octet (stride < 2^18, so the sum cannot wrap for nocts < 2^31)
     const uint32_t nxt = oct + stride;
     ld_quad(nxt < no, boards2, actions4, override4, HAS_OVERRIDE, 2u * nxt, xa, xb, ax, ox);
-    if (__builtin_expect(stream_quad<HAS_OVERRIDE>(sbase, one, p4, ya, yb, ay, oy, w.z, w.w, 2u * oct + 1u, next2,
-                                                   reward4, flags4), 0))
-      fix_quad<HAS_OVERRIDE>(2u * oct + 1u, boards2, actions4, next2, reward4, flags4, glut, keys, step, index_base,
-                             p4, override4);
+    if (__builtin_expect((stream_quad<HAS_OVERRIDE>(sbase, one, p4, ya, yb, ay, oy, w.z, w.w, 2u * oct + 1u, next2,
+                                                    reward4, flags4) & OVF4) != 0u, 0))
+    {   // the quad index is rebuilt from live values behind an opaque asm: ptxas otherwise keeps (spills) 2 * oct + 1
+      uint32_t o;
+      asm volatile("sub.u32 %0, %1, %2;" : "=r"(o) : "r"(nxt), "r"(stride));
+      fix_quad<HAS_OVERRIDE>(2u * o + 1u);
+    }
     oct = nxt;
   }
 }
