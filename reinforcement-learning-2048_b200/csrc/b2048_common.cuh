@@ -25,12 +25,6 @@ constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
 #ifndef B2048_V_SWZ
 #define B2048_V_SWZ 1
 #endif
-#ifndef B2048_V_SPAWN_SUFFIX
-#define B2048_V_SPAWN_SUFFIX 2  // k-th empty cell: 2 = exclusive prefix counts from one IMAD.WIDE per half + zero-nibble test, 1 = suffix counts (IMAD.HI), 0 = round-1 form (shifted masks, prefix counts, equality test)
-#endif
-#ifndef B2048_V_SPAWN_SHIFT
-#define B2048_V_SPAWN_SHIFT 1   // insert the spawned tile with a variable shift (0: IMAD.HI; A/B: 0.318 vs 0.324 ms)
-#endif
 constexpr int LUT_SWZ_SHIFT = 6;
 constexpr uint32_t LUT_SWZ_MASK = B2048_V_SWZ ? 31u : 0u;
 __host__ __device__ constexpr uint32_t lut_swizzle(uint32_t i) { return i ^ ((i >> LUT_SWZ_SHIFT) & LUT_SWZ_MASK); }
@@ -364,6 +358,14 @@ __device__ __forceinline__ void spawn_kth_empty(uint32_t& lo, uint32_t& hi, uint
 // over multiples of n's power of two, so P(4) is exact to 2^-13 and independent of k; each cell's
 // probability differs from 1/n by at most 2^-16.  One Philox call now serves eight boards: the step
 // kernel's per-board cost of the generator drops from 10 to 5 instructions.
+// The cell: one IMAD.WIDE per half of the board turns the bit-3 mask e3 of its empty nibbles into exclusive prefix
+// counts (low word of e3 * 0x22222222: nibble i = #{empty j < i}) AND inclusive suffix counts (high word); their
+// sum is the half's total in every nibble.  The cell of rank k is the empty cell whose exclusive prefix count
+// equals k: x = k * 0x11111111 - prefix is zero exactly in the nibbles with that count (the counts rise
+// monotonically along the board, so the borrows run through the nibbles ABOVE the target only and the nibbles
+// below stay positive), and "zero nibble AND empty" is the cell -- two LOP3 per word.  (Round 1 / early round 2:
+// shifted masks, inclusive prefix counts by two multiplies and a three-LOP3 equality test per word;
+// tests/test_swar_model.py checks both forms against each other for every occupancy pattern.)
 // DLOW: D holds the lane value d itself (low half) instead of d << 16; the product is then taken with
 // cnt << 16, which the replicated count word provides for free (same 64-bit product, one LOP3 less).
 template <class A = Add7, bool DLOW = false>
@@ -371,18 +373,6 @@ __device__ __forceinline__ void spawn_draw16(uint32_t& lo, uint32_t& hi, uint32_
                                              A add = A()) {
   const uint32_t e3_lo = ~(add(lo & 0x77777777u) | lo) & 0x88888888u;  // bit 3 of empty nibbles
   const uint32_t e3_hi = ~(add(hi & 0x77777777u) | hi) & 0x88888888u;
-#if B2048_V_SPAWN_SUFFIX
-  // Inclusive SUFFIX counts per nibble straight from the bit-3 masks: hi32(e3 * 0x22222222) puts
-  // #{empty cells j >= i} into nibble i (one IMAD.HI on the FMA pipe, no ">> 3" on the ALU pipe).  The cell
-  // of row-major rank k is the empty cell whose suffix count equals cnt - k; subtracting (cnt - k) from every
-  // nibble makes exactly the nibbles with that count zero (the suffix counts fall monotonically along the
-  // word, so the borrows run through the nibbles below the target only, and the hi word needs no borrow-in
-  // from the lo word for the same reason), and "zero nibble AND empty" is the chosen cell: two LOP3 per word
-  // instead of three (tests/test_swar_model.py checks every occupancy pattern against the prefix form).
-#if B2048_V_SPAWN_SUFFIX == 2
-  // exclusive prefix counts (low word of the product) and inclusive suffix counts (high word) from ONE
-  // IMAD.WIDE per half; their sum is the half's total in every nibble.  The chosen cell is the empty cell
-  // whose exclusive prefix count equals k: x = k - prefix is zero exactly there.
   uint32_t q_lo, q_hi, r_lo, r_hi;
   mulhilo32(e3_lo, 0x22222222u, q_hi, q_lo);
   mulhilo32(e3_hi, 0x22222222u, r_hi, r_lo);
@@ -392,48 +382,18 @@ __device__ __forceinline__ void spawn_draw16(uint32_t& lo, uint32_t& hi, uint32_
   mulhilo32(D, cnt, k, frac);
   const uint32_t km = k * 0x11111111u;
   const uint32_t x_lo = km - q_lo, x_hi = km - ep_hi;
-#else
-  if (DLOW) D <<= 16;
-  const uint32_t s_hi = __umulhi(e3_hi, 0x22222222u);
-  const uint32_t s_lo = __umulhi(e3_lo, 0x22222222u) + (s_hi & 15u) * 0x11111111u;
-  const uint32_t cnt = s_lo & 15u;
-  uint32_t k, frac;
-  mulhilo32(D, cnt, k, frac);
-  const uint32_t d = (k - cnt) * 0x11111111u;
-  const uint32_t x_lo = s_lo + d, x_hi = s_hi + d;
-#endif
   uint32_t h_lo, h_hi;                                                 // bit 3 of the chosen nibble
   {
     const uint32_t t_lo = add(x_lo & 0x77777777u), t_hi = add(x_hi & 0x77777777u);
     asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(h_lo) : "r"(t_lo), "r"(x_lo), "r"(e3_lo));   // ~(t | x) & e3
     asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(h_hi) : "r"(t_hi), "r"(x_hi), "r"(e3_hi));
   }
-#else
-  if (DLOW) D <<= 16;
-  const uint32_t e_lo = (e3_lo >> 3), e_hi = (e3_hi >> 3);
-  const uint32_t p_lo = e_lo * 0x11111111u;                            // inclusive prefix counts per nibble
-  const uint32_t c_lo = (p_lo >> 28);
-  const uint32_t p_hi = e_hi * 0x11111111u + c_lo * 0x11111111u;
-  const uint32_t cnt = (p_hi >> 28);
-  uint32_t k, frac;
-  mulhilo32(D, cnt, k, frac);
-  const uint32_t tgt = k * 0x11111111u + 0x11111111u;                  // (k+1) in every nibble
-  const uint32_t h_lo = ~ne3_dirty(p_lo, tgt, add) & e3_lo;            // bit 3 of the chosen nibble
-  const uint32_t h_hi = ~ne3_dirty(p_hi, tgt, add) & e3_hi;
-#endif
-#if B2048_V_SPAWN_SHIFT
-  const uint32_t sh = (frac < p4) ? 2u : 3u;                           // bit 3 -> bit 1 ("4") or bit 0 ("2")
+  // insert with a variable shift: bit 3 -> bit 1 ("4") or bit 0 ("2").  (IMAD.HI with e << 29: 0.324 vs 0.318 ms)
+  const uint32_t sh = (frac < p4) ? 2u : 3u;
   if (changed) {
     lo += h_lo >> sh;
     hi += h_hi >> sh;
   }
-#else
-  const uint32_t e29 = (frac < p4) ? (2u << 29) : (1u << 29);          // hi32(h * (e << 29)) = (h >> 3) * e
-  if (changed) {
-    lo = __umulhi(h_lo, e29) + lo;
-    hi = __umulhi(h_hi, e29) + hi;
-  }
-#endif
 }
 
 // lane l (0..7) of a Philox result, as D = d << 16

@@ -81,13 +81,10 @@ constexpr int STREAM_THREADS = B2048_STREAM_THREADS;
 // table reads use explicit shared-space loads on a 32-bit base address computed once: with generic
 // pointers ptxas re-derived the shared window base (S2R + MOV + LEA) for every board.
 constexpr uint32_t SM_ACT = (uint32_t)LUT_SMEM_BYTES;   // 4 rows x 32 B: per-action transform constants
-#ifndef B2048_V_FLAGIDP
-#define B2048_V_FLAGIDP 1   // 1: the RIGHT / OVERFLOW bits of the four table entries index the flags table through ONE IDP.4A
-#endif
-// flags byte per (action, frame mask): 4 rows x 32 B; with B2048_V_FLAGIDP 16 such blocks, one per combination of the
-// RIGHT / OVERFLOW bits of row pairs (0,1) and (2,3)
+// flags byte per (action, frame mask): 16 blocks of 4 rows x 32 B, one block per combination of the RIGHT / OVERFLOW
+// bits of the table entries of rows (0,2) and rows (1,3) -- those bits index the block through ONE IDP.4A
 constexpr uint32_t SM_LEGAL = SM_ACT + 128;
-constexpr uint32_t SM_LEGAL_BYTES = B2048_V_FLAGIDP ? 2048 : 128;
+constexpr uint32_t SM_LEGAL_BYTES = 2048;
 constexpr uint32_t SM_CONST = SM_LEGAL + SM_LEGAL_BYTES;  // run-time constants (StreamConsts)
 constexpr uint32_t SM_BAR = SM_CONST + 32;              // mbarrier
 constexpr uint32_t SM_COLD = SM_BAR + 16;               // ColdArgs: the kernel arguments the cold path needs
@@ -108,55 +105,25 @@ struct ColdArgs {
 constexpr int STREAM_SMEM_BYTES = (int)(SM_COLD + ((sizeof(ColdArgs) + 15) & ~size_t(15)));
 static_assert(STREAM_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 
-// Instruction selection in stream_board follows measurements on B200 (profiles/ubench):
-// the integer ALU pipe (LOP3/SHF/PRMT/ISETP/SEL/VIMNMX) issues one warp instruction per 2 cycles and is
-// the busiest unit, the FMA pipe (IMAD, IDP) has room.  So table addresses and 16-bit extracts are
-// integer dot products (IDP.2A/4A: "half-word * 4 + base" in one FMA-pipe instruction, no PRMT/LEA),
-// the "+0x7777.." of the nibble tests is an IMAD through a run-time 1, and selectors go to PRMT raw.
-#ifndef B2048_V_CCONST
-#define B2048_V_CCONST 1   // 1: IDP weights of the per-board action offsets as constant-bank operands (no UMOV per board)
-#endif
-#if B2048_V_CCONST
-__constant__ uint32_t c_saw[4] = {0x20u, 0x2000u, 0x200000u, 0x20000000u};
-__constant__ uint32_t c_kw[4] = {0x04000004u, 0x01000000u, 0x0404u, 0x08000200u};
-#endif
-#ifndef B2048_V_DLOW
-#define B2048_V_DLOW 1
-#endif
-#ifndef B2048_V_REGCONST
-#define B2048_V_REGCONST 1   // 1: dot-product weights and p4 live in registers (read once from shared memory, opaque to ptxas)
-#endif
-// run-time copies of constants: `one` feeds Add7Fma; with B2048_V_REGCONST the IDP weights and the spawn
-// threshold too, so that ptxas does not re-materialise them (UMOV / LDC) for every board
+// Instruction selection in the streaming kernels follows measurements on B200 (profiles/ubench):
+// a warp scheduler issues a mixed ALU / FMA-pipe stream at ~0.7 instructions per cycle and the integer ALU pipe
+// (LOP3/SHF/PRMT/ISETP/SEL/VIMNMX, one warp instruction per 2 cycles) is the busiest unit, so the code is written
+// for FEW instructions first and for FMA-pipe forms second: table addresses and 16-bit extracts are integer dot
+// products (IDP.2A/4A: "half-word * 4 + base" in one instruction, no PRMT/LEA), the "+0x7777.." of the nibble
+// tests is an IMAD through a run-time 1, and selectors go to PRMT raw.
+// Weights that differ per board position come from the constant bank as direct operands (an immediate would be
+// re-materialised by one UMOV per use); the weights every board uses live in registers (StreamConsts), read once
+// from shared memory so that ptxas cannot see through them (it otherwise re-creates them with UMOV / LDC per board).
+__constant__ uint32_t c_saw[4] = {0x20u, 0x2000u, 0x200000u, 0x20000000u};   // byte j of the actions word * 32
+__constant__ uint32_t c_wfl = 0x08000200u;                                     // flags block: byte 1 * 2 + byte 3 * 8
 struct StreamConsts {
   uint32_t one, p4, k4, k16, k44;
-#if B2048_V_FLAGIDP == 2
-  uint32_t kfl;
-#endif
 };
-#if B2048_V_FLAGIDP == 2
-#define K_WFL(k) (k).kfl
-#elif B2048_V_CCONST
-#define K_WFL(k) c_kw[3]
-#else
-#define K_WFL(k) 0x08000200u
-#endif
-#if B2048_V_CCONST == 2
-#define K_W4(k) c_kw[0]
-#define K_W16(k) c_kw[1]
-#define K_W44(k) c_kw[2]
-#define K_P4(k, p4) (k).p4
-#elif B2048_V_REGCONST
+#define K_WFL(k) c_wfl
 #define K_W4(k) (k).k4
 #define K_W16(k) (k).k16
 #define K_W44(k) (k).k44
 #define K_P4(k, p4) (k).p4
-#else
-#define K_W4(k) 0x04000004u
-#define K_W16(k) 0x01000000u
-#define K_W44(k) 0x0404u
-#define K_P4(k, p4) (p4)
-#endif
 #define SHR16(x) __dp2a_hi((x), K_W16(kc), 0u)   // x >> 16 as (high half * 1) on the FMA pipe
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -191,9 +158,8 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
   }
   if (threadIdx.x == 0) {
     uint32_t* k = reinterpret_cast<uint32_t*>(smem_raw + SM_CONST);
-    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4; k[5] = 0x08000200u;
+    k[0] = 0x04000004u; k[1] = 1u; k[2] = 0x01000000u; k[3] = 0x0404u; k[4] = p4;
   }
-#if B2048_V_FLAGIDP
   // block = R01 + 2 * O01 + 4 * R23 + 8 * O23 (bits 14 / 15 of the entries' upper halves, times the IDP weights 2 and 8
   // of bytes 1 and 3); inside a block: 32 * action + changed + 2 * up + 4 * down
   for (uint32_t t = threadIdx.x; t < SM_LEGAL_BYTES; t += blockDim.x) {
@@ -203,14 +169,6 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
     smem_raw[SM_LEGAL + t] = (uint8_t)(zframe_to_legal((int)a, zm) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
                                        (ovf ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
   }
-#else
-  if (threadIdx.x < 128) {
-    const uint32_t a = threadIdx.x >> 5, m = threadIdx.x & 31u;
-    smem_raw[SM_LEGAL + threadIdx.x] =
-        (uint8_t)(zframe_to_legal((int)a, m & 15u) | ((m & 1u) ? (uint32_t)B2048_FLAG_CHANGED : 0u) |
-                  ((m & 16u) ? (uint32_t)B2048_FLAG_OVERFLOW : 0u));
-  }
-#endif
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, (uint32_t)LUT_SMEM_BYTES);
@@ -221,11 +179,10 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
   }
 }
 
-// One board of the streaming kernel.  `sa` = shared base + 32 * action (row of both small tables).
-// Same arithmetic as slide_board + finish_board (b2048_common.cuh), specialised for the
-// shared-memory map above; the flags byte incl. CHANGED comes straight from the legal table.
+// The streaming kernel's per-board arithmetic is slide_board + finish_board (b2048_common.cuh) specialised for the
+// shared-memory map above; the flags byte incl. CHANGED comes straight from the flags table.
 //
-// There is no branch in here.  Rows outside the staged part of the table (top cell >= 2^14, never seen
+// There is no branch per board.  Rows outside the staged part of the table (top cell >= 2^14, never seen
 // in play) are clamped to the LAST staged row, 0xDFFF = cells [15,15,15,13]: that row merges 32768+32768,
 // so its table entry carries the OVERFLOW bit and a clamped lookup simply raises B2048_FLAG_OVERFLOW in
 // the flags byte.  The caller redoes every quad that shows the flag from the full table in global memory
@@ -233,100 +190,9 @@ __device__ __forceinline__ void stage_tables(unsigned char* smem_raw, uint64_t* 
 // four boards lets ptxas overlap the shared-memory latency of one board with the arithmetic of the others.
 constexpr uint32_t LUT_LIM2 = ((uint32_t)LUT_SMEM_ROWS - 1u) * 0x00010001u;   // last staged row, both halves
 static_assert(LUT_SMEM_ROWS - 1 == 0xDFFF, "the clamp row must be one whose entry has the OVERFLOW bit");
-template <bool HAS_OVERRIDE, bool DLOW = false>
-__device__ __forceinline__ void stream_board(uint32_t sbase, uint32_t sa,
-                                             uint32_t lo, uint32_t hi, uint32_t D, uint32_t p4, uint32_t ovr,
-                                             uint32_t& olo, uint32_t& ohi, uint32_t& reward, uint32_t& flags,
-                                             const StreamConsts& kc) {
-  const uint32_t one = kc.one;
-  const uint4 xa = lds128(sa + SM_ACT);        // sel_fwd_lo, sel_fwd_hi, sel_inv_lo, sel_inv_hi
-  const uint4 xb = lds128(sa + SM_ACT + 16);   // mul_l, shift, mask, -
-  uint32_t zl = prmt_raw(lo, hi, xa.x);
-  uint32_t zh = prmt_raw(lo, hi, xa.y);
-  {
-    const uint32_t tl = (zl ^ (zl >> xb.y)) & xb.z, th = (zh ^ (zh >> xb.y)) & xb.z;
-    zl ^= tl ^ (tl * xb.x);
-    zh ^= th ^ (th * xb.x);
-  }
-  uint32_t e0, e1, e2, e3;
-  {
-    const uint32_t cl = __vminu2(zl, LUT_LIM2), ch = __vminu2(zh, LUT_LIM2);
-    // bank swizzle of both rows at once, then row * 4 + base as ONE integer dot product (FMA pipe):
-    // halves of the word times bytes {4,0} / {0,4}
-    const uint32_t sl = cl ^ ((cl >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
-    const uint32_t sh = ch ^ ((ch >> LUT_SWZ_SHIFT) & (LUT_SWZ_MASK * 0x00010001u));
-#ifdef B2048_DIAG_NOLDS
-    e0 = __dp2a_lo(sl, 0x04000004u, sbase) * 0x9E3779B1u;
-    e1 = __dp2a_hi(sl, 0x04000004u, sbase) * 0x9E3779B1u;
-    e2 = __dp2a_lo(sh, 0x04000004u, sbase) * 0x9E3779B1u;
-    e3 = __dp2a_hi(sh, 0x04000004u, sbase) * 0x9E3779B1u;
-#else
-    e0 = lds32(__dp2a_lo(sl, K_W4(kc), sbase));
-    e1 = lds32(__dp2a_hi(sl, K_W4(kc), sbase));
-    e2 = lds32(__dp2a_lo(sh, K_W4(kc), sbase));
-    e3 = lds32(__dp2a_hi(sh, K_W4(kc), sbase));
-#endif
-  }
-  uint32_t wl = __byte_perm(e0, e1, 0x5410);
-  uint32_t wh = __byte_perm(e2, e3, 0x5410);
-  const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
-  const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
-  const uint32_t fl = h01 | h23;
-  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));   // 4 * sum of 14-bit fields
 
-  // legality of the input board in the transformed frame (see slide_board)
-  const uint32_t changed = (wl ^ zl) | (wh ^ zh);
-  const Add7Fma add{one};
-  const uint32_t n_l = nz3(zl, add), n_h = nz3(zh, add);
-  const uint32_t v_l = __byte_perm(zl, zh, 0x5432), v_h = SHR16(zh);
-  const uint32_t ne_l = ne3_dirty(zl, v_l, add), ne_h = ne3_dirty(zh, v_h, add);
-  const uint32_t nv_l = __byte_perm(n_l, n_h, 0x5432), nv_h = SHR16(n_h);
-#ifdef B2048_DIAG_NOPERP
-  const uint32_t up = 0, dn_l = 0, dn_h = 0; (void)n_l; (void)n_h; (void)ne_l; (void)ne_h; (void)nv_l; (void)nv_h;
-#else
-  const uint32_t up = (nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h));
-  const uint32_t dn_l = n_l & ~(nv_l & ne_l), dn_h = n_h & ~(nv_h & ne_h);
-#endif
-  // table index built on top of the row address with five predicated adds (no SEL, no final add)
-#if B2048_V_FLAGIDP
-  uint32_t fa = __dp4a(fl & 0xC000C000u, K_WFL(kc), sa);   // + 128 * (R01 + 2 O01 + 4 R23 + 8 O23)
-  if (changed) fa += 1u;
-  if (up) fa += 2u;
-  if (dn_l | (dn_h & 0x0000FFFFu)) fa += 4u;
-#else
-  uint32_t fa = sa;
-  if (changed) fa += 1u;
-  if (fl & 0x40004000u) fa += 2u;
-  if (up) fa += 4u;
-  if (dn_l | (dn_h & 0x0000FFFFu)) fa += 8u;
-  if (fl & 0x80008000u) fa += 16u;
-#endif
-#ifdef B2048_DIAG_NOFLAGS
-  flags = changed ? 1u : 0u; (void)fa;
-#else
-  flags = lds8(fa + SM_LEGAL);                 // legal | DONE | CHANGED | OVERFLOW
-#endif
-
-  {
-    const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
-    wl ^= tl ^ (tl * xb.x);
-    wh ^= th ^ (th * xb.x);
-  }
-  olo = prmt_raw(wl, wh, xa.z);
-  ohi = prmt_raw(wl, wh, xa.w);
-#ifdef B2048_DIAG_NOSPAWN
-  olo ^= changed ? D : 0u;
-#else
-  finish_board<HAS_OVERRIDE, Add7Fma, DLOW>(olo, ohi, changed, D, K_P4(kc, p4), ovr, flags, add);
-#endif
-}
-
-#ifndef B2048_V_PAIRLEGAL
-#define B2048_V_PAIRLEGAL 1
-#endif
-#if B2048_V_PAIRLEGAL
 // ---- two boards at a time ------------------------------------------------------------------------------------
-// Same arithmetic as stream_board, split into three phases so that the perpendicular legality of TWO boards can
+// Three phases (slide, pair step, finish) so that the perpendicular legality of TWO boards can
 // share one word: the vertical pairs (row 0, row 1) and (row 1, row 2) of a board fill its low word, the third pair
 // (row 2, row 3) only half of the high word -- the third pairs of boards A and B are packed into one word
 // ([row2_A, row2_B] against [row3_A, row3_B]): three words of nibble tests per two boards instead of four.
@@ -397,7 +263,6 @@ __device__ __forceinline__ void board_finish(const BoardMid& m, uint32_t D,
   ohi = m.ohi;
   finish_board<HAS_OVERRIDE, Add7Fma, DLOW>(olo, ohi, m.changed, D, K_P4(kc, p4), ovr, flags, add);
 }
-#endif
 
 // Cold path of the streaming kernel: recompute the four boards of one quad with the full table in
 // global memory (same arithmetic as step_small_kernel) and overwrite the quad's outputs.
@@ -456,22 +321,12 @@ __device__ __forceinline__ uint32_t stream_quad(uint32_t sbase, const StreamCons
                                             uint32_t quad, uint4* __restrict__ next2, uint4* __restrict__ reward4,
                                             uint32_t* __restrict__ flags4) {
   const uint32_t a32 = a4 & 0x03030303u;     // byte j * 32 + base = one IDP.4A per board
-#if B2048_V_CCONST
 #define SA_OF(j) __dp4a(a32, c_saw[j], sbase)
-#else
-#define SA_OF(j) __dp4a(a32, 0x20u << (8 * (j)), sbase)
-#endif
   uint32_t n0l, n0h, n1l, n1h, n2l, n2h, n3l, n3h, rw0, rw1, rw2, rw3, f, fw;
   // draws: 16-bit lanes of the octet's Philox words, moved to the upper half (low lane first);
   // the four flag bytes are packed as they arrive (one live register instead of four)
-  // (odd lanes hand their draw over in the low half: B2048_V_DLOW, see spawn_draw16)
-#if B2048_V_DLOW
+  // odd lanes hand their draw over in the low half (DLOW, see spawn_draw16): one IDP instead of a mask
 #define D_ODD(w) __dp2a_hi((w), K_W16(one), 0u)
-#else
-#define D_ODD(w) ((w) & 0xFFFF0000u)
-#endif
-#if B2048_V_PAIRLEGAL
-  static_assert(B2048_V_FLAGIDP == 1 && B2048_V_DLOW == 1, "the pair path assumes the current defaults");
   {
     BoardMid ma, mb;
     const uint32_t sa0 = SA_OF(0), sa1 = SA_OF(1);
@@ -493,17 +348,6 @@ __device__ __forceinline__ uint32_t stream_quad(uint32_t sbase, const StreamCons
     board_finish<HAS_OVERRIDE, true>(mb, D_ODD(w_hi), p4, o4 >> 24, n3l, n3h, f, one);
     fw += f * 16777216u;
   }
-#else
-  stream_board<HAS_OVERRIDE>(sbase, SA_OF(0), ba.x, ba.y, w_lo << 16, p4, o4 & 0xFFu, n0l, n0h, rw0, fw, one);
-  stream_board<HAS_OVERRIDE, B2048_V_DLOW != 0>(sbase, SA_OF(1), ba.z, ba.w, D_ODD(w_lo), p4, (o4 >> 8) & 0xFFu, n1l, n1h,
-                                                rw1, f, one);
-  fw += f * 256u;
-  stream_board<HAS_OVERRIDE>(sbase, SA_OF(2), bb.x, bb.y, w_hi << 16, p4, (o4 >> 16) & 0xFFu, n2l, n2h, rw2, f, one);
-  fw += f * 65536u;
-  stream_board<HAS_OVERRIDE, B2048_V_DLOW != 0>(sbase, SA_OF(3), bb.z, bb.w, D_ODD(w_hi), p4, o4 >> 24, n3l, n3h, rw3, f,
-                                                one);
-  fw += f * 16777216u;
-#endif
 #undef D_ODD
 #undef SA_OF
   st_stream_v8(next2 + 2u * quad, make_uint4(n0l, n0h, n1l, n1h), make_uint4(n2l, n2h, n3l, n3h));
@@ -564,9 +408,6 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     const uint4 k = lds128(sbase + SM_CONST);
     one.one = k.y; one.k4 = k.x; one.k16 = k.z; one.k44 = k.w;
     one.p4 = lds32(sbase + SM_CONST + 16);
-#if B2048_V_FLAGIDP == 2
-    one.kfl = lds32(sbase + SM_CONST + 20);
-#endif
   }
 
   constexpr uint32_t OVF4 = B2048_FLAG_OVERFLOW * 0x01010101u;
@@ -575,11 +416,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
 
     // one Philox4x32-7 call per aligned group of EIGHT global board indices (16-bit lanes)
     const uint64_t pidx = pidx_base + oct;
-#ifdef B2048_DIAG_NOPHILOX
-    uint4 w = make_uint4((uint32_t)pidx * 0x9E3779B9u, (uint32_t)pidx * 0x85EBCA6Bu, s_lo * 0xC2B2AE35u ^ (uint32_t)pidx, (uint32_t)pidx * 0x27D4EB2Fu);
-#else
     uint4 w = philox4x32_10<SPAWN_PHILOX_ROUNDS>(make_uint4((uint32_t)pidx, (uint32_t)(pidx >> 32), s_lo, s_hi), keys);
-#endif
     if (base_mis != 0) {  // uniform: index_base not a multiple of 8 -> the octet straddles two calls
       const uint64_t p1 = pidx + 1;
       const uint4 w1 = philox4x32_10<SPAWN_PHILOX_ROUNDS>(make_uint4((uint32_t)p1, (uint32_t)(p1 >> 32), s_lo, s_hi), keys);

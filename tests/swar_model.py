@@ -87,3 +87,41 @@ def spawn_kth_empty(lo, hi, w_pos, e):
     h_lo = (~ne3_dirty(p_lo, tgt)) & e3_lo
     h_hi = (~ne3_dirty(p_hi, tgt)) & e3_hi
     return (lo + (h_lo >> 3) * e) & M32, (hi + (h_hi >> 3) * e) & M32, cnt
+
+
+def spawn_draw16_prefix_form(lo, hi, D):
+    """Round-1 form of spawn_draw16's cell choice: shifted masks, inclusive prefix counts, equality test.
+    -> (bit-3 mask of the chosen nibble in lo, in hi, frac)"""
+    e3_lo = (~(((lo & 0x77777777) + 0x77777777) | lo)) & 0x88888888
+    e3_hi = (~(((hi & 0x77777777) + 0x77777777) | hi)) & 0x88888888
+    e_lo, e_hi = e3_lo >> 3, e3_hi >> 3
+    p_lo = (e_lo * 0x11111111) & M32
+    c_lo = p_lo >> 28
+    p_hi = (e_hi * 0x11111111 + c_lo * 0x11111111) & M32
+    cnt = p_hi >> 28
+    prod = D * cnt
+    k, frac = prod >> 32, prod & M32
+    tgt = (k * 0x11111111 + 0x11111111) & M32
+    return (~ne3_dirty(p_lo, tgt)) & e3_lo, (~ne3_dirty(p_hi, tgt)) & e3_hi, frac
+
+
+def spawn_draw16(lo, hi, D, dlow=False):
+    """The device function spawn_draw16 (b2048_common.cuh) bit for bit: exclusive prefix / inclusive suffix counts
+    from one wide multiply per half, x = k - prefix, zero-nibble test.  dlow: D = d instead of d << 16."""
+    e3_lo = (~(((lo & 0x77777777) + 0x77777777) | lo)) & 0x88888888
+    e3_hi = (~(((hi & 0x77777777) + 0x77777777) | hi)) & 0x88888888
+    q = e3_lo * 0x22222222
+    r = e3_hi * 0x22222222
+    q_lo, q_hi, r_lo, r_hi = q & M32, q >> 32, r & M32, r >> 32
+    ep_hi = (r_lo + q_lo + q_hi) & M32
+    cnt = ((ep_hi + r_hi) & M32) & (0x000F0000 if dlow else 15)
+    prod = D * cnt
+    assert prod < 1 << 64
+    k, frac = prod >> 32, prod & M32
+    km = (k * 0x11111111) & M32
+    x_lo, x_hi = (km - q_lo) & M32, (km - ep_hi) & M32
+
+    def zero_and_empty(x, e3):
+        t = ((x & 0x77777777) + 0x77777777) & M32
+        return (~(t | x)) & e3 & M32
+    return zero_and_empty(x_lo, e3_lo), zero_and_empty(x_hi, e3_hi), frac

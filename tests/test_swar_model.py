@@ -70,3 +70,35 @@ def test_lut_bank_swizzle_is_a_bijection_that_spreads_the_banks():
 
     plain, swz = wavefronts(rows), wavefronts(rows ^ ((rows >> 6) & 31))
     assert plain > 5.5 and swz < 4.0, (plain, swz)
+
+
+def test_spawn_cell_choice_every_occupancy_pattern():
+    """spawn_draw16 picks the empty cell of row-major rank k = floor(d * n / 65536): the device form (prefix and
+    suffix counts from one wide multiply per half, zero-nibble test, optional low-half draw) against the round-1
+    form and against a plain loop, for every occupancy pattern with at least one tile and draws on both sides of
+    every rank boundary."""
+    rng = np.random.default_rng(5)
+    for pat in range(1, 1 << 16):                 # bit i = cell i occupied
+        lo = hi = 0
+        vals = rng.integers(1, 16, size=16)
+        for i in range(8):
+            if pat >> i & 1:
+                lo |= int(vals[i]) << (4 * i)
+            if pat >> (8 + i) & 1:
+                hi |= int(vals[8 + i]) << (4 * i)
+        empties = [i for i in range(16) if not pat >> i & 1]
+        n = len(empties)
+        ds = {0, 65535, int(rng.integers(0, 65536))}
+        for j in range(1, n):                     # smallest d of rank j and the one before it
+            d = (j * 65536 + n - 1) // n
+            ds.update((d - 1, min(d, 65535)))
+        for d in ds:
+            want = sm.spawn_draw16_prefix_form(lo, hi, d << 16)
+            assert sm.spawn_draw16(lo, hi, d << 16) == want, (hex(pat), d)
+            assert sm.spawn_draw16(lo, hi, d, dlow=True) == want, (hex(pat), d)
+            if n:
+                cell = empties[(d * n) >> 16]
+                h = (want[0] | (want[1] << 32)) >> 3
+                assert h == 1 << (4 * cell), (hex(pat), d)
+            else:
+                assert want[0] == 0 and want[1] == 0
