@@ -224,7 +224,9 @@ __device__ __forceinline__ void board_slide(uint32_t sbase, uint32_t sa, uint32_
   reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));
   m.changed = (wl ^ zl) | (wh ^ zh);
   m.fa = __dp4a((h01 | h23) & 0xC000C000u, K_WFL(kc), sa);   // + 128 * (R01 + 2 O01 + 4 R23 + 8 O23)
-  if (m.changed) m.fa += 1u;
+  // "+ 1 if changed" as an in-place predicated add: written in C++, ptxas builds fa + 1 in a second register and
+  // moves the old value back under the inverse predicate (one instruction more per board)
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(m.fa) : "r"(m.changed));
   m.zl = zl; m.zh = zh;
   {  // back to the board's own frame (the spawn comes after the pair step)
     const uint32_t tl = (wl ^ (wl >> xb.y)) & xb.z, th = (wh ^ (wh >> xb.y)) & xb.z;
