@@ -24,6 +24,7 @@ distribution, rollouts, the end-to-end trainer, the link probe and the reference
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -63,14 +64,25 @@ def f64_peak_tflops():
         return 37.2, "derived: 148 SMs x 128 flop/clk x 1.965 GHz"
 
 
+def kernel_source_sha16():
+    """Hash of the sources the dominant kernel is compiled from: ties the committed ncu traffic figure to a kernel version."""
+    h = hashlib.sha256()
+    for name in ("env_kernels.cu", "b2048_common.cuh"):
+        with open(os.path.join(ROOT, "reinforcement-learning-2048_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic_per_launch():
-    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture, and whether that capture
+    was taken on the kernel sources of this tree (profiles/step_stream_traffic.json records their hash)."""
     try:
         with open(os.path.join(ROOT, "profiles", "step_stream_traffic.json")) as f:
             d = json.load(f)
-        return float(d["dram_bytes_per_launch"]) * (BOARDS_PER_GPU / float(d["boards_per_launch"]))
+        return (float(d["dram_bytes_per_launch"]) * (BOARDS_PER_GPU / float(d["boards_per_launch"])),
+                d.get("kernel_source_sha16") == kernel_source_sha16(), d.get("source"))
     except Exception:
-        return None
+        return None, False, None
 
 
 class ClockSampler(threading.Thread):
@@ -533,6 +545,7 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         k_ms = statistics.mean(kernel_ms)
         achieved = n * BYTES_PER_STEP / (k_ms * 1e-3) / 1e9
+        traffic, traffic_ok, traffic_src = ncu_traffic_per_launch()
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -548,7 +561,8 @@ def run_ours(args):
                     "link_ceiling_steps_per_sec": e2e_link["e2e_ceiling_steps_per_sec"]},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
+                         "frac": achieved / peak, "traffic": traffic, "traffic_from_this_kernel_version": traffic_ok,
+                         "traffic_source": traffic_src,
                          "kernel": "step_stream_kernel<false>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": n * BYTES_PER_STEP, "peak_source": peak_src,
                          "peak_spec": HBM_SPEC_GBS, "frac_vs_spec": achieved / HBM_SPEC_GBS,
