@@ -249,7 +249,8 @@ __device__ __forceinline__ void fill_tabs(SmemTabs* t) {
 //   bits  0-15 result row            bits 16-29 merge reward / 4
 //   bit  30    the row can move RIGHT (toward nibble 3)      bit 31 overflow (32768+32768)
 // Row 0xEEEE (reward/4 = 0x4000) does not fit 14 bits; it is never in the shared-memory part
-// (top nibble 14) and the global path adds its 65536 separately.
+// (top nibble 14) and the global path adds its 65536 separately.  The shared-memory copy additionally marks every
+// row with reward/4 >= 2^12 as OVERFLOW (host_api.cu: staged_entry), which sends its quad to the global path.
 constexpr uint32_t ENTRY_RIGHT = 0x40000000u, ENTRY_OVF = 0x80000000u;
 
 // Look the four transformed rows up in the full table in global memory (L2-resident, 256 KB).  Used by

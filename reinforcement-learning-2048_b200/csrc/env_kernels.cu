@@ -221,7 +221,9 @@ __device__ __forceinline__ void board_slide(uint32_t sbase, uint32_t sa, uint32_
   uint32_t wh = __byte_perm(e2, e3, 0x5410);
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
-  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));
+  // 4 * sum of the reward/4 fields: staged entries keep them below 2^12, so the flag bits of the unmasked halves land
+  // at bit 16 and above and ONE mask after the two dot products replaces one per operand (host_api.cu: staged_entry)
+  reward = __dp2a_lo(h23, K_W44(kc), __dp2a_lo(h01, K_W44(kc), 0u)) & 0xFFFFu;
   m.changed = (wl ^ zl) | (wh ^ zh);
   m.fa = __dp4a((h01 | h23) & 0xC000C000u, K_WFL(kc), sa);   // + 128 * (R01 + 2 O01 + 4 R23 + 8 O23)
   // "+ 1 if changed" as an in-place predicated add: written in C++, ptxas builds fa + 1 in a second register and

@@ -65,6 +65,15 @@ static uint32_t build_row_entry(uint32_t row) {
   return res | (r4 << 16) | (can_right ? 0x40000000u : 0u) | (overflow ? 0x80000000u : 0u);
 }
 
+// The staged (shared-memory) copy keeps reward/4 below 2^12 (bits 28-29 zero), so that the streaming kernel can
+// sum the four rows' upper halves UNMASKED -- 4 * sum(reward/4) stays below 2^16 and the RIGHT / OVERFLOW bits land
+// at bit 16 and above -- and mask once after the sum.  A row whose merges are worth 16384 or more (two 8192 tiles, or
+// two pairs of 4096 tiles: never seen in play) gets the OVERFLOW bit instead: its quad is redone from the plain table.
+static uint32_t staged_entry(uint32_t e) {
+  const uint32_t r4 = (e >> 16) & 0x3FFFu;
+  return r4 < 4096u ? e : ((e & 0xCFFFFFFFu) | ENTRY_OVF);
+}
+
 static const std::vector<uint32_t>& host_lut() {
   if (g_host_lut.empty()) {
     g_host_lut.resize(LUT_ROWS);
@@ -133,7 +142,7 @@ extern "C" int b2048_init(int device) {
   const std::vector<uint32_t>& lut = host_lut();
   std::vector<uint32_t> both(lut.begin(), lut.end());      // plain table, then the swizzled smem image
   both.resize(LUT_ROWS + LUT_SMEM_ROWS);
-  for (uint32_t i = 0; i < (uint32_t)LUT_SMEM_ROWS; ++i) both[LUT_ROWS + lut_swizzle(i)] = lut[i];
+  for (uint32_t i = 0; i < (uint32_t)LUT_SMEM_ROWS; ++i) both[LUT_ROWS + lut_swizzle(i)] = staged_entry(lut[i]);
   if ((e = cudaMalloc(&c->lut, both.size() * sizeof(uint32_t))) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpy(c->lut, both.data(), both.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) !=
       cudaSuccess)
