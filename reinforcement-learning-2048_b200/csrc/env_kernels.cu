@@ -556,7 +556,7 @@ __device__ __forceinline__ void slide_fixed(uint32_t sbase, const StreamConsts& 
   const uint32_t h01 = __byte_perm(e0, e1, 0x7632);
   const uint32_t h23 = __byte_perm(e2, e3, 0x7632);
   fl |= h01 | h23;
-  reward = __dp2a_lo(h23 & 0x3FFF3FFFu, K_W44(kc), __dp2a_lo(h01 & 0x3FFF3FFFu, K_W44(kc), 0u));
+  reward = __dp2a_lo(h23, K_W44(kc), __dp2a_lo(h01, K_W44(kc), 0u)) & 0xFFFFu;   // staged entries: reward/4 < 2^12 (board_slide)
   changed = (wl ^ zl) | (wh ^ zh);
   if (A != 2) {
     wl = delta_swap(wl, x);
