@@ -8,11 +8,15 @@ are accumulated per board on the device.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
-from . import ddqn, env
+from . import _lib, ddqn, env
 from .qfused import FusedConvQ
 from .replay import ReplayRing
+
+_U64 = (1 << 64) - 1
 
 
 class VectorEnv:
@@ -40,6 +44,24 @@ class VectorEnv:
         self.totals = torch.zeros(4, dtype=torch.int64, **kw)          # games, merge-score sum, moves sum
         self.qmean_sum = torch.zeros(1, dtype=torch.float64, **kw)     # sum over games of mean max-Q
         self.max_tile_hist = torch.zeros(16, dtype=torch.int64, **kw)
+        # step() is launch-bound on the host below ~1 Mi games (4 096 games: 75 us of Python per step against ~25 us
+        # of kernels): it calls the C-ABI directly with raw addresses of these persistent buffers, validated here once,
+        # instead of going through the checking wrappers of env.py five times per step
+        self._dev = env._dev(self.boards)
+        _lib.init(self._dev)
+        self._L = _lib.lib()
+        self._p = {name: getattr(self, name).data_ptr() for name in
+                   ("boards", "next_boards", "reward", "flags", "legal", "actions", "max_q", "q", "ep_score", "ep_moves",
+                    "ep_qsum", "totals", "qmean_sum", "max_tile_hist")}
+
+    def _rebind(self) -> None:
+        """Re-validate and re-read the buffer addresses after a caller assigned new tensors."""
+        for name, dtype in (("boards", torch.int64), ("next_boards", torch.int64)):
+            env._chk(getattr(self, name), dtype, self.n, name)
+            if env._dev(getattr(self, name)) != self._dev:
+                raise ValueError(f"{name} moved to another device")
+        for name in self._p:
+            self._p[name] = getattr(self, name).data_ptr()
 
     def observe(self) -> torch.Tensor:
         """Network input of the current boards: float64 [n,1,4,4] (conv) or [n,16] (dense)."""
@@ -50,29 +72,44 @@ class VectorEnv:
     def step(self, model=None, epsilon: float = 1.0, replay: ReplayRing | None = None):
         """One step of every game.  model=None or epsilon>=1 plays the uniformly random policy of
         the reference's epsilon branch (illegal no-op moves included, src/dqn_lib.py:20-21)."""
+        if torch.cuda.current_device() != self._dev:
+            with torch.cuda.device(self._dev):
+                return self._step(model, epsilon, replay)
+        return self._step(model, epsilon, replay)
+
+    def _step(self, model, epsilon, replay):
         self.t += 1
+        L, p, n, t, base, chk = self._L, self._p, self.n, self.t, self.index_base & _U64, _lib.check
+        if p["boards"] != self.boards.data_ptr() or p["next_boards"] != self.next_boards.data_ptr():
+            self._rebind()                                   # a caller replaced the board tensors (e.g. a restored checkpoint)
+        st = torch.cuda.current_stream(self.device).cuda_stream
         greedy = model is not None and epsilon < 1.0
         if greedy:
-            env.legal_mask(self.boards, out=self.legal)
+            chk(L.b2048_legal_mask(p["boards"], p["legal"], n, st), "b2048_legal_mask")
             if isinstance(model, FusedConvQ):                # one fused kernel straight from the packed boards
                 q = model.forward_boards(self.boards, out=self.q)
             else:
                 q = model(self.observe()).contiguous()
-            ddqn.egreedy_select(q, self.legal, epsilon, seed=self.seed ^ 0x5EED, ctr=self.t,
-                                index_base=self.index_base, out=(self.actions, self.max_q))
+            if q.dtype != torch.float64 or q.numel() != 4 * n:
+                raise ValueError("the model must return float64 Q-values [n, 4]")
+            chk(L.egreedy_select(q.data_ptr(), p["legal"], float(epsilon), (self.seed ^ 0x5EED) & _U64, t, base, None,
+                                 p["actions"], p["max_q"], n, st), "egreedy_select")
         else:
-            env.random_actions(self.n, seed=self.seed ^ 0xAC71, step_index=self.t, index_base=self.index_base,
-                               out=self.actions)
-        env.step(self.boards, self.actions, seed=self.seed, step_index=self.t, index_base=self.index_base,
-                 p4=self.p4, out=(self.next_boards, self.reward, self.flags))
+            chk(L.b2048_random_actions(p["actions"], n, (self.seed ^ 0xAC71) & _U64, t, base, st), "b2048_random_actions")
+        chk(L.b2048_step(p["boards"], p["actions"], p["next_boards"], p["reward"], p["flags"], n, self.seed & _U64, t, base,
+                         self.p4, None, st), "b2048_step")
         if replay is not None:
-            replay.append(self.boards, self.actions, self.reward, self.next_boards, self.flags)
+            if replay._dev != self._dev:
+                raise ValueError("the replay ring lives on another device")
+            chk(L.replay_append(ctypes.byref(replay._ring), p["boards"], p["actions"], p["reward"], p["next_boards"],
+                                p["flags"], n, st), "replay_append")
         # one fused pass: per-game accumulators, totals of finished games, fresh boards for them
-        env.episode_end(self.next_boards, self.boards, self.reward, self.flags, self.max_q if greedy else None,
-                        self.ep_score, self.ep_moves, self.ep_qsum, self.totals, self.qmean_sum,
-                        self.max_tile_hist, seed=self.seed ^ 0x4E57, step_index=self.t, index_base=self.index_base,
-                        p4=self.p4)
+        chk(L.b2048_episode_end(p["next_boards"], p["boards"], p["reward"], p["flags"], p["max_q"] if greedy else None,
+                                p["ep_score"], p["ep_moves"], p["ep_qsum"], p["totals"], p["qmean_sum"],
+                                p["max_tile_hist"], n, (self.seed ^ 0x4E57) & _U64, t, base, self.p4, st),
+            "b2048_episode_end")
         self.boards, self.next_boards = self.next_boards, self.boards
+        p["boards"], p["next_boards"] = p["next_boards"], p["boards"]
         return self.flags
 
     def stats(self) -> dict:

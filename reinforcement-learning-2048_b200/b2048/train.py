@@ -75,19 +75,26 @@ class _LaggedCounter:
         self.dev = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(self.slots)]
         self.host = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(self.slots)]
         self.events = [torch.cuda.Event() for _ in range(self.slots)]
+        self.dev0 = [d[:1] for d in self.dev]             # views made once: the loop is launch-bound on the host
+        self.dev1 = [d[1:] for d in self.dev]
+        self.host0 = [h[:1] for h in self.host]
         self.t = 0
 
     def push(self, counter: torch.Tensor) -> None:
+        """`counter`: a one-element int64 device tensor (a persistent view, e.g. venv.totals[:1])."""
         i = self.t % self.slots
-        d = self.dev[i]
-        d[0].copy_(counter)
-        if self.err_source is not None:                   # K5's sticky error flag rides along, negated for MIN
-            d[1].copy_(-self.err_source)
+        if self.world == 1 and self.err_source is None:
+            self.host0[i].copy_(counter, non_blocking=True)   # one 8-byte copy; the error word of the slot stays 0
         else:
-            d[1].zero_()
-        if self.world > 1:
-            dist.all_reduce(d, op=dist.ReduceOp.MIN)      # asynchronous w.r.t. the host: enqueued on the stream
-        self.host[i].copy_(d, non_blocking=True)
+            d = self.dev[i]
+            self.dev0[i].copy_(counter)
+            if self.err_source is not None:               # K5's sticky error flag rides along, negated for MIN
+                self.dev1[i].copy_(-self.err_source)
+            else:
+                self.dev1[i].zero_()
+            if self.world > 1:
+                dist.all_reduce(d, op=dist.ReduceOp.MIN)  # asynchronous w.r.t. the host: enqueued on the stream
+            self.host[i].copy_(d, non_blocking=True)
         self.events[i].record()
         self.t += 1
 
@@ -136,10 +143,11 @@ def train_batched(model: torch.nn.Module, cfg: TrainConfig, device="cuda", log_e
         episodes = finished
         return crossings
 
+    finished_games = venv.totals[:1]                       # persistent view of the device counter
     while episodes < cfg.no_episodes:
         venv.step(model=updater.i_model, epsilon=epsilon_for(episodes, cfg), replay=ring)
         steps += 1
-        counter.push(venv.totals[0])
+        counter.push(finished_games)
         seen = counter.pop()
         if seen is None:
             continue
