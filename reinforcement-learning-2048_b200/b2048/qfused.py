@@ -129,9 +129,10 @@ def conv_q_forward_update(x, x_next, params, target_params, want_online_next=Tru
 def conv_q_backward(saved, params, gq, out=None):
     """Gradients of the eight parameter tensors given gq = d loss / d q [n,4]: per layer the K7 weight /
     bias gradient kernels on the saved matrices (on a side stream: they are leaves of the dependency chain
-    g4 -> g3 -> g2 -> g1), the K8 tensor-core kernel for the input gradients (fused with the ReLU masks; round 1:
-    cuBLAS DGEMMs + ATen threshold_backward) and one fused kernel for the first convolution.  `out` (optional): eight contiguous tensors in parameter order that
-    receive the gradients (overwritten, not accumulated) — e.g. the views of a flat gradient buffer."""
+    g4 -> g3 -> g2 -> g1), tensor-core kernels for the input gradients, fused with the ReLU masks (fc1's is stored
+    regrouped as (board, position) x channel rows; conv2's never leaves the accumulators: the first convolution's whole
+    backward is applied to it in the same kernel).  No library GEMM.  `out` (optional): eight contiguous tensors in
+    parameter order that receive the gradients (overwritten, not accumulated) — e.g. the views of a flat gradient buffer."""
     x, p2, a2, a3 = saved
     w2, w3, w4 = params[2], params[4], params[6]
     n = x.shape[0]
@@ -214,8 +215,8 @@ class _ConvQTrain(torch.autograd.Function):
 
 
 class TrainableConvQ(nn.Module):
-    """The reference's conv Q-network as a module whose forward is K6 and whose backward is K7 + cuBLAS
-    (`_ConvQTrain`); without gradients it is the plain fused forward.  Wraps the caller's nn.Sequential:
+    """The reference's conv Q-network as a module whose forward is K6 and whose backward is K7 + the fused
+    input-gradient kernels (`_ConvQTrain`); without gradients it is the plain fused forward.  Wraps the caller's nn.Sequential:
     the parameters are its own tensors."""
 
     def __init__(self, net: nn.Sequential):

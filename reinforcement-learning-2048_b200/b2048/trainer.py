@@ -1,6 +1,7 @@
 """Double-DQN updates at scale, captured in one CUDA graph: GPU replay sampling (K2), the float64
-Q-network forwards (conv config: the fused kernel K6, with saved activations for Q(s); otherwise torch),
-fused target / loss (K3), backward (conv config: K7 weight gradients + cuBLAS), gradient exchange + Adam
+Q-network forwards (conv config: ONE launch of the fused kernel K6 for Q(s) with saved activations, Q_online(s')
+and Q_target(s'); dense config: K8; otherwise torch), fused target / loss (K3), backward (conv: K7 weight gradients +
+fused input-gradient kernels; dense: K8; no library GEMM in either), gradient exchange + Adam
 (one GPU: fused Adam kernel; several: the NVLink peer-memory kernel K5, or NCCL).
 
 `DDQNUpdater.update()` is the "real" update (zero_grad -> backward -> allreduce -> step); the
@@ -140,7 +141,7 @@ class DDQNUpdater:
                 self.ring.head_size, self.loss)
 
     def _capture(self):
-        """Warm-up (allocator, cuBLAS plans) + graph capture, WITHOUT side effects: the three warm-up
+        """Warm-up (allocator, lazy kernel configuration) + graph capture, WITHOUT side effects: the three warm-up
         updates are real ones, so the state they touch is saved before and put back after — the first
         `update()` in graph mode then applies exactly one optimizer step, and a resumed run continues
         bit-identically (with several ranks every rank runs the same warm-up exchanges, so the
