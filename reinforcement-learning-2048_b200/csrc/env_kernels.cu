@@ -821,6 +821,24 @@ __global__ void random_actions_kernel(uint8_t* __restrict__ actions, int64_t n, 
   actions[i] = (uint8_t)(w >> 30);
 }
 
+// The same actions, sixteen per thread: a Philox call serves the four boards g, g+1, g+2, g+3 of an aligned group (words
+// x, y, z, w), so a thread makes four calls and stores one 128-bit word instead of sixteen threads making the same
+// four calls four times over for one byte each (64 Mi actions: 259 us with the kernel above).  Needs index_base % 4 == 0
+// and a 16-byte aligned array; the host wrapper sends the unaligned head / tail to the kernel above.
+__global__ void random_actions16_kernel(uint4* __restrict__ actions16, int64_t n16, uint64_t seed, uint64_t step,
+                                        uint64_t index_base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint64_t q0 = (index_base >> 2) + 4ull * (uint64_t)i;      // first of this thread's four Philox counters
+  uint32_t w[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 r = philox_at(seed, DOM_ACTIONS, q0 + c, step);
+    w[c] = (r.x >> 30) | ((r.y >> 30) << 8) | ((r.z >> 30) << 16) | ((r.w >> 30) << 24);
+  }
+  actions16[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- one board per call: the engine behind the drop-in board.Board2048 (BASELINE config 1) --------------------------
 // Board2048.peek_action / available_moves / available_moves_as_torch_unit_vector / _populate_empty_cell / __init__
 // (src/board.py:10-20, 41-51, 128-202) for ONE board: tile values come in as a kernel argument, the result goes to
@@ -1156,8 +1174,25 @@ extern "C" int b2048_random_actions(uint8_t* actions, int64_t n, uint64_t seed, 
   if (!actions) return B2048_EINVAL;
   B2048_CTX_OR_RETURN();
   (void)ctx;
-  random_actions_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      actions, n, seed, step, index_base);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // head up to the first index that is a multiple of 4 at a 16-byte aligned address (if the two ever coincide), body in
+  // groups of sixteen, tail
+  int64_t head = n;
+  for (int64_t h = 0; h < 16 && h < n; ++h)
+    if (((index_base + (uint64_t)h) & 3u) == 0 && ((reinterpret_cast<uintptr_t>(actions) + (uintptr_t)h) & 15u) == 0) {
+      head = h;
+      break;
+    }
+  const int64_t n16 = (n - head) / 16;
+  if (head > 0)
+    random_actions_kernel<<<(unsigned)blocks_for(head, 256), 256, 0, st>>>(actions, head, seed, step, index_base);
+  if (n16 > 0)
+    random_actions16_kernel<<<(unsigned)blocks_for(n16, 256), 256, 0, st>>>(reinterpret_cast<uint4*>(actions + head), n16,
+                                                                           seed, step, index_base + (uint64_t)head);
+  const int64_t done = head + 16 * n16;
+  if (done < n)
+    random_actions_kernel<<<(unsigned)blocks_for(n - done, 256), 256, 0, st>>>(actions + done, n - done, seed, step,
+                                                                              index_base + (uint64_t)done);
   return (int)cudaGetLastError();
 }
 
