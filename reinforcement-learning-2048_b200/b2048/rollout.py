@@ -47,6 +47,7 @@ class VectorEnv:
         # step() is launch-bound on the host below ~1 Mi games (4 096 games: 75 us of Python per step against ~25 us
         # of kernels): it calls the C-ABI directly with raw addresses of these persistent buffers, validated here once,
         # instead of going through the checking wrappers of env.py five times per step
+        self._ever_greedy = False
         self._dev = env._dev(self.boards)
         _lib.init(self._dev)
         self._L = _lib.lib()
@@ -104,10 +105,12 @@ class VectorEnv:
             chk(L.replay_append(ctypes.byref(replay._ring), p["boards"], p["actions"], p["reward"], p["next_boards"],
                                 p["flags"], n, st), "replay_append")
         # one fused pass: per-game accumulators, totals of finished games, fresh boards for them
+        # (the max-Q accumulators stay out of the pass until the first model-driven step: 16 of 45 bytes per game)
+        self._ever_greedy = self._ever_greedy or greedy
         chk(L.b2048_episode_end(p["next_boards"], p["boards"], p["reward"], p["flags"], p["max_q"] if greedy else None,
-                                p["ep_score"], p["ep_moves"], p["ep_qsum"], p["totals"], p["qmean_sum"],
-                                p["max_tile_hist"], n, (self.seed ^ 0x4E57) & _U64, t, base, self.p4, st),
-            "b2048_episode_end")
+                                p["ep_score"], p["ep_moves"], p["ep_qsum"] if self._ever_greedy else None, p["totals"],
+                                p["qmean_sum"] if self._ever_greedy else None, p["max_tile_hist"], n,
+                                (self.seed ^ 0x4E57) & _U64, t, base, self.p4, st), "b2048_episode_end")
         self.boards, self.next_boards = self.next_boards, self.boards
         p["boards"], p["next_boards"] = p["next_boards"], p["boards"]
         return self.flags
