@@ -65,12 +65,23 @@ def f64_peak_tflops():
 
 
 def kernel_source_sha16():
-    """Hash of the sources the dominant kernel is compiled from: ties the committed ncu traffic figure to a kernel version."""
+    """Hash of the dominant kernel's machine code (the SASS of step_stream_kernel<false> in the built library, addresses
+    and encodings included): ties the committed ncu traffic figure to a kernel version.  Falls back to a hash of the
+    kernel's source files where cuobjdump is missing."""
+    lib = os.path.join(ROOT, "reinforcement-learning-2048_b200", "b2048", "libb2048.so")
+    try:
+        import subprocess
+        sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=120).stdout
+        for block in sass.split("Function : ")[1:]:
+            if "step_stream_kernelILb0" in block.split("\n", 1)[0]:
+                return "sass:" + hashlib.sha256(block.split("\n", 1)[1].encode()).hexdigest()[:16]
+    except Exception:
+        pass
     h = hashlib.sha256()
     for name in ("env_kernels.cu", "b2048_common.cuh"):
         with open(os.path.join(ROOT, "reinforcement-learning-2048_b200", "csrc", name), "rb") as f:
             h.update(f.read())
-    return h.hexdigest()[:16]
+    return "src:" + h.hexdigest()[:16]
 
 
 def ncu_traffic_per_launch():
