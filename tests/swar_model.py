@@ -125,3 +125,29 @@ def spawn_draw16(lo, hi, D, dlow=False):
         t = ((x & 0x77777777) + 0x77777777) & M32
         return (~(t | x)) & e3 & M32
     return zero_and_empty(x_lo, e3_lo), zero_and_empty(x_hi, e3_hi), frac
+
+
+def perp_legal_single(zl, zh):
+    """Perpendicular legality of ONE transformed board, the one-board form of slide_board: (toward row 0, toward row 3)."""
+    n_l, n_h = nz3(zl), nz3(zh)
+    v_l, v_h = byte_perm(zl, zh, 0x5432), zh >> 16
+    ne_l, ne_h = ne3_dirty(zl, v_l), ne3_dirty(zh, v_h)
+    nv_l, nv_h = byte_perm(n_l, n_h, 0x5432), n_h >> 16
+    up = ((nv_l & ~(n_l & ne_l)) | (nv_h & ~(n_h & ne_h))) & M32
+    dn_l, dn_h = (n_l & ~(nv_l & ne_l)) & M32, (n_h & ~(nv_h & ne_h)) & M32
+    return bool(up), bool(dn_l | (dn_h & 0xFFFF))
+
+
+def perp_legal_pair(a, b):
+    """The streaming kernel's pair step (env_kernels.cu: pair_legal) for two transformed boards a = (zl, zh),
+    b = (zl, zh): the third vertical pairs of both boards share one word.  -> ((upA, dnA), (upB, dnB))."""
+    P, Q = byte_perm(a[1], b[1], 0x5410), byte_perm(a[1], b[1], 0x7632)      # rows 2 / rows 3 of A and B
+    nP, nQ, neP = nz3(P), nz3(Q), ne3_dirty(P, Q)
+    up3, dn3 = (nQ & ~(nP & neP)) & M32, (nP & ~(nQ & neP)) & M32
+    out = []
+    for (zl, zh), sel, half in ((a, 0x5432, 0x0000FFFF), (b, 0x7632, 0xFFFF0000)):
+        n, v = nz3(zl), byte_perm(zl, zh, 0x5432)
+        ne = ne3_dirty(zl, v)
+        nv = byte_perm(n, nP, sel)
+        out.append((bool(((nv & ~(n & ne)) | (up3 & half)) & M32), bool(((n & ~(nv & ne)) | (dn3 & half)) & M32)))
+    return tuple(out)

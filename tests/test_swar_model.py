@@ -102,3 +102,30 @@ def test_spawn_cell_choice_every_occupancy_pattern():
                 assert h == 1 << (4 * cell), (hex(pat), d)
             else:
                 assert want[0] == 0 and want[1] == 0
+
+
+def test_pair_step_equals_the_single_board_legality():
+    """The streaming kernel tests the vertical row pairs of TWO boards in three words (third pairs packed together):
+    same answers as the one-board form and as a plain column scan, on random boards (sparse to full, tiles up to
+    32768) and on structured ones."""
+    rng = np.random.default_rng(11)
+
+    def scan(zl, zh):
+        rows = [zl & 0xFFFF, zl >> 16, zh & 0xFFFF, zh >> 16]
+        cell = lambda r, c: (rows[r] >> (4 * c)) & 15
+        up = any(cell(r + 1, c) and (cell(r, c) == 0 or cell(r, c) == cell(r + 1, c)) for r in range(3) for c in range(4))
+        dn = any(cell(r, c) and (cell(r + 1, c) == 0 or cell(r, c) == cell(r + 1, c)) for r in range(3) for c in range(4))
+        return up, dn
+
+    boards = [(0, 0), (0xFFFFFFFF, 0xFFFFFFFF), (0x12341234, 0x12341234), (0x00010000, 0), (0, 0x00010000),
+              (0x43211234, 0x43211234), (0x21212121, 0x12121212), (0x0000FFFF, 0), (0, 0xFFFF0000)]
+    for p_empty in (0.0, 0.3, 0.7, 0.95):
+        for _ in range(600):
+            cells = np.where(rng.random(16) < p_empty, 0, rng.integers(1, 16, size=16))
+            v = sum(int(c) << (4 * i) for i, c in enumerate(cells))
+            boards.append((v & 0xFFFFFFFF, v >> 32))
+    for i in range(0, len(boards) - 1):
+        a, b = boards[i], boards[(i * 7 + 3) % len(boards)]
+        got = sm.perp_legal_pair(a, b)
+        assert got[0] == sm.perp_legal_single(*a) == scan(*a), (hex(a[0]), hex(a[1]))
+        assert got[1] == sm.perp_legal_single(*b) == scan(*b), (hex(b[0]), hex(b[1]))
