@@ -331,25 +331,23 @@ __device__ __forceinline__ uint32_t stream_quad(uint32_t sbase, const StreamCons
   // the four flag bytes are packed as they arrive (one live register instead of four)
   // odd lanes hand their draw over in the low half (DLOW, see spawn_draw16): one IDP instead of a mask
 #define D_ODD(w) __dp2a_hi((w), K_W16(one), 0u)
+  // all four boards are slid before the two pair steps and the four finishes: the same instructions as pair after
+  // pair, but ptxas interleaves more independent work around the shared-memory lookups (0.2845 against 0.2862 ms)
   {
-    BoardMid ma, mb;
-    const uint32_t sa0 = SA_OF(0), sa1 = SA_OF(1);
+    BoardMid ma, mb, mc, md;
+    const uint32_t sa0 = SA_OF(0), sa1 = SA_OF(1), sa2 = SA_OF(2), sa3 = SA_OF(3);
     board_slide(sbase, sa0, ba.x, ba.y, ma, rw0, one);
     board_slide(sbase, sa1, ba.z, ba.w, mb, rw1, one);
+    board_slide(sbase, sa2, bb.x, bb.y, mc, rw2, one);
+    board_slide(sbase, sa3, bb.z, bb.w, md, rw3, one);
     pair_legal(ma, mb, one);
+    pair_legal(mc, md, one);
     board_finish<HAS_OVERRIDE, false>(ma, w_lo << 16, p4, o4 & 0xFFu, n0l, n0h, fw, one);
     board_finish<HAS_OVERRIDE, true>(mb, D_ODD(w_lo), p4, (o4 >> 8) & 0xFFu, n1l, n1h, f, one);
     fw += f * 256u;
-  }
-  {
-    BoardMid ma, mb;
-    const uint32_t sa2 = SA_OF(2), sa3 = SA_OF(3);
-    board_slide(sbase, sa2, bb.x, bb.y, ma, rw2, one);
-    board_slide(sbase, sa3, bb.z, bb.w, mb, rw3, one);
-    pair_legal(ma, mb, one);
-    board_finish<HAS_OVERRIDE, false>(ma, w_hi << 16, p4, (o4 >> 16) & 0xFFu, n2l, n2h, f, one);
+    board_finish<HAS_OVERRIDE, false>(mc, w_hi << 16, p4, (o4 >> 16) & 0xFFu, n2l, n2h, f, one);
     fw += f * 65536u;
-    board_finish<HAS_OVERRIDE, true>(mb, D_ODD(w_hi), p4, o4 >> 24, n3l, n3h, f, one);
+    board_finish<HAS_OVERRIDE, true>(md, D_ODD(w_hi), p4, o4 >> 24, n3l, n3h, f, one);
     fw += f * 16777216u;
   }
 #undef D_ODD
