@@ -62,6 +62,13 @@ class FusedConvQ:
                 _stream(ref)), "qnet_conv_forward_f64")
         return out
 
+    def forward_boards_raw(self, boards_ptr: int, out_ptr: int, n: int, stream: int) -> None:
+        """forward_boards ("log2" scaling) on raw device addresses of buffers the caller has validated (int64 [n] packed
+        boards, float64 [n, 4] output, on this network's device, which must be current): the launch-bound rollout loop
+        (`VectorEnv.step`) calls this once per step."""
+        _lib.check(_lib.lib().qnet_conv_forward_f64(boards_ptr, None, SCALINGS["log2"], *[p.data_ptr() for p in self._params],
+                                                    out_ptr, n, stream), "qnet_conv_forward_f64")
+
     @torch.no_grad()
     def forward_boards(self, boards: torch.Tensor, scaling: str = "log2", out=None) -> torch.Tensor:
         """Q[n,4] for packed boards; `scaling` picks the input the network sees: "log2" = exponents

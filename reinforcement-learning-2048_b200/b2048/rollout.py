@@ -87,13 +87,15 @@ class VectorEnv:
         greedy = model is not None and epsilon < 1.0
         if greedy:
             chk(L.b2048_legal_mask(p["boards"], p["legal"], n, st), "b2048_legal_mask")
-            if isinstance(model, FusedConvQ):                # one fused kernel straight from the packed boards
-                q = model.forward_boards(self.boards, out=self.q)
+            if isinstance(model, FusedConvQ) and model.device == self.boards.device:
+                model.forward_boards_raw(p["boards"], p["q"], n, st)      # one fused kernel straight from the packed boards
+                q_ptr = p["q"]
             else:
                 q = model(self.observe()).contiguous()
-            if q.dtype != torch.float64 or q.numel() != 4 * n:
-                raise ValueError("the model must return float64 Q-values [n, 4]")
-            chk(L.egreedy_select(q.data_ptr(), p["legal"], float(epsilon), (self.seed ^ 0x5EED) & _U64, t, base, None,
+                if q.dtype != torch.float64 or q.numel() != 4 * n or q.device != self.boards.device:
+                    raise ValueError("the model must return float64 Q-values [n, 4] on the environment's device")
+                q_ptr = q.data_ptr()
+            chk(L.egreedy_select(q_ptr, p["legal"], float(epsilon), (self.seed ^ 0x5EED) & _U64, t, base, None,
                                  p["actions"], p["max_q"], n, st), "egreedy_select")
         else:
             chk(L.b2048_random_actions(p["actions"], n, (self.seed ^ 0xAC71) & _U64, t, base, st), "b2048_random_actions")
