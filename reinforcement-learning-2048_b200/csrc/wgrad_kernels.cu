@@ -237,6 +237,115 @@ int64_t wt_blocks(int64_t rows, int sms) {
   return b;
 }
 
+// ---- the same product for K = 256, one QUARTER of the 64 x 256 result per CTA -------------------------------------
+// With one full 64 x 256 partial result per CTA the 148 CTAs write 19 MB of partial sums for a 131 KB result, and the
+// reduce pass reads them back (12 us for the second convolution's gradient, as long as a third of the product itself).
+// Here blockIdx.y picks a quadrant (32 channels x 128 columns) and blockIdx.x a row range four times as long: the same
+// work per CTA, a quarter of the partial sums (37 instead of 148 per output), four times fewer, longer main loops.
+// Warp w owns columns [n0 + 16 w, + 16) x the quadrant's 32 channels = 4 x 2 accumulator tiles (6 fragment loads per
+// 8 DMMAs).  Same shared-memory layout and strides as wgrad_dmma_kernel; only the quadrant's columns are staged.
+__global__ void __launch_bounds__(256, 1)
+    wgrad_dmma_quad_kernel(const double* __restrict__ g, const double* __restrict__ x, double* __restrict__ partials,
+                           int64_t rows, int64_t rows_per_cta) {
+  constexpr int K = 256, O = 64 * K;
+  extern __shared__ __align__(16) double wsm[];
+  __shared__ double bsum[7][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+  const int m0 = 32 * (blockIdx.y & 1), n0 = 128 * (blockIdx.y >> 1);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+
+  auto stage = [&](int buf, int64_t t0) {     // rows [t0, t0+32) -> buffer `buf`; rows past r1 become zeros
+    double* gs = wsm + buf * WT_BUF;
+    double* xs = gs + WT_ROWS * WT_GS;
+    for (int i = tid; i < WT_ROWS * 16; i += 256) {          // g: 16 chunks of 2 doubles per row (32 channels)
+      const int r = i >> 4, c2 = m0 + (i & 15) * 2;
+      if (t0 + r < r1) cp_async16(gs + r * WT_GS + c2, g + (t0 + r) * 64 + c2);
+      else gs[r * WT_GS + c2] = gs[r * WT_GS + c2 + 1] = 0.0;
+    }
+    for (int i = tid; i < WT_ROWS * 64; i += 256) {          // x: 64 chunks per row (128 columns)
+      const int r = i >> 6, c2 = n0 + (i & 63) * 2;
+      if (t0 + r < r1) cp_async16(xs + r * WT_XS + c2, x + (t0 + r) * K + c2);
+      else xs[r * WT_XS + c2] = xs[r * WT_XS + c2 + 1] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  double acc[4][2][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  double accb = 0.0;               // bias gradient (quadrants with n0 == 0): thread = (channel m0 + tid % 32, rows 4 * (tid / 32) .. + 3)
+
+  int buf = 0;
+  if (r0 < r1) stage(0, r0);
+  for (int64_t t0 = r0; t0 < r1; t0 += WT_ROWS) {
+    if (t0 + WT_ROWS < r1) {
+      stage(buf ^ 1, t0 + WT_ROWS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double* gs = wsm + buf * WT_BUF;
+    const double* xs = gs + WT_ROWS * WT_GS;
+    const int ksteps = (int)(r1 - t0 < WT_ROWS ? (r1 - t0 + 3) / 4 : WT_ROWS / 4);
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+      // A[m = channel][k = row] = g[row][channel];  B[k = row][n = column] = x[row][column]
+      const double* ga = gs + (ks * 4 + fk) * WT_GS + m0 + fr;
+      const double* xb = xs + (ks * 4 + fk) * WT_XS + n0 + warp * 16 + fr;
+      const double b0 = xb[0], b1 = xb[8];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const double a = ga[mt * 8];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[mt][0][0]), "+d"(acc[mt][0][1]) : "d"(a), "d"(b0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[mt][1][0]), "+d"(acc[mt][1][1]) : "d"(a), "d"(b1));
+      }
+    }
+    if (n0 == 0) {
+      const double* gb = gs + (tid >> 5) * 4 * WT_GS + m0 + (tid & 31);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) accb += gb[r * WT_GS];
+    }
+    __syncthreads();          // everyone is done with `buf` before the next iteration refills it
+    buf ^= 1;
+  }
+  double* mine = partials + (int64_t)blockIdx.x * (O + 64);
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)   // C fragment: row = fr, columns 2*fk, 2*fk+1 of the tile
+      *reinterpret_cast<double2*>(mine + (m0 + mt * 8 + fr) * K + n0 + warp * 16 + nt * 8 + 2 * fk) =
+          make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+  if (n0 == 0) {
+    if (tid >= 32) bsum[(tid >> 5) - 1][tid & 31] = accb;
+    __syncthreads();
+    if (tid < 32) {
+      double t = accb;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) t += bsum[j][tid];
+      mine[O + m0 + tid] = t;
+    }
+  }
+}
+
+// row ranges of the quartered kernel: a quarter of the SMs' worth of ranges, each a multiple of 4 rows
+void wtq_plan(int64_t rows, int sms, int64_t* rows_per_cta, int64_t* chunks) {
+  int64_t c = sms / 4;
+  const int64_t tiles = (rows + WT_ROWS - 1) / WT_ROWS;
+  if (c > tiles) c = tiles;
+  if (c < 1) c = 1;
+  const int64_t per = ((rows + c - 1) / c + 3) / 4 * 4;
+  *rows_per_cta = per;
+  *chunks = (rows + per - 1) / per;
+}
+// K = 256 with enough rows to give every quadrant CTA at least two tiles: the quartered kernel
+bool wt_quartered(int64_t rows, int K, int sms) { return K == 256 && rows >= (int64_t)(sms / 4) * 2 * WT_ROWS; }
+
 // ---- first convolution of the conv Q-network: col2im + ReLU mask + weight / bias gradient in one pass ----
 // Backward of "conv1 -> ReLU -> im2col" given gp2 = d loss / d patches2 [4n, 256] (row = board*4 + conv2
 // position, column = channel*4 + tap) and the forward patches2 (the ReLU mask: every entry that reads a
@@ -582,6 +691,11 @@ extern "C" int64_t layer_wgrad64_scratch_elems(int64_t rows, int K) {
   int err = 0;
   DeviceCtx* ctx = current_ctx(&err);
   if (!ctx || rows <= 0 || K <= 0) return 0;
+  if (wt_quartered(rows, K, ctx->sm_count)) {
+    int64_t per, chunks;
+    wtq_plan(rows, ctx->sm_count, &per, &chunks);
+    return chunks * (64 * (int64_t)K + 64);
+  }
   return wt_blocks(rows, ctx->sm_count) * (64 * (int64_t)K + 64);
 }
 
@@ -594,9 +708,14 @@ extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, d
   DeviceCtx* ctx = current_ctx(&err);
   if (!ctx) return err;
   int64_t blocks, rows_per_cta;
-  wt_plan(rows, ctx->sm_count, &rows_per_cta, &blocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K, rows_per_cta);
+  if (wt_quartered(rows, K, ctx->sm_count)) {
+    wtq_plan(rows, ctx->sm_count, &rows_per_cta, &blocks);
+    wgrad_dmma_quad_kernel<<<dim3((unsigned)blocks, 4), 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, rows_per_cta);
+  } else {
+    wt_plan(rows, ctx->sm_count, &rows_per_cta, &blocks);
+    wgrad_dmma_kernel<<<(unsigned)blocks, 256, WT_SMEM_BYTES, st>>>(g, x, scratch, rows, K, rows_per_cta);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int O = 64 * K;
@@ -607,6 +726,8 @@ extern "C" int layer_wgrad64_f64(const double* g, const double* x, double* dw, d
 namespace b2048 {
 cudaError_t wgrad_kernels_configure() {
   cudaError_t e = cudaFuncSetAttribute(wgrad_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(wgrad_dmma_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(cb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM_BYTES);
   if (e != cudaSuccess) return e;
